@@ -1,0 +1,182 @@
+/*
+ * vilgod_b200 -- C ABI of the B200-native (sm_100a) ViLGOD classification hot path.
+ *
+ * Drop-in boundary.  Each entry point names the reference interface it
+ * replaces (paths relative to the chreisinger/ViLGOD tree):
+ *
+ *   vg_create / vg_destroy       RealisticProjection.__init__   src/utils/mv_utils.py:133-171
+ *                                (view table, Gaussian weights, projection parameters)
+ *   vg_load_vit_weights          clip.load / build_model        third_party/CLIP/clip/clip.py:94-142,
+ *                                                               third_party/CLIP/clip/model.py:399-436
+ *   vg_set_text_features         ClipWrapper.__init__           src/utils/clip_utils.py:21-26
+ *   vg_project                   RealisticProjection.get_img    src/utils/mv_utils.py:173-187
+ *                                + upsample/uint8 glue          src/vilgod/zero_shot_detector.py:405-409
+ *                                + CLIP preprocess (folded)     third_party/CLIP/clip/clip.py:79-86
+ *   vg_encode_score              ClipWrapper.predict_clip_labels src/utils/clip_utils.py:34-63
+ *                                (CLIP.encode_image             third_party/CLIP/clip/model.py:223-240,340)
+ *   vg_vote                      LidarFrame.update_object_classes src/vilgod/lidar_frame.py:260-291
+ *                                + 24->4 class mapping          src/vilgod/zero_shot_detector.py:412-415
+ *   vg_classify                  the loop body of ZeroShotDetector.classification
+ *                                                               src/vilgod/zero_shot_detector.py:389-416
+ *
+ * Conventions
+ *   - plain C, no torch types.  Every pointer named d_* is a DEVICE pointer supplied by the caller;
+ *     the library owns no caller-visible tensors.  The handle owns only converted weights (bf16
+ *     copies, folded patch-embed), TMA descriptors and the view table.
+ *   - all work is enqueued on the caller's stream (a cudaStream_t passed as void*); no internal
+ *     synchronisation except in vg_create / vg_load_vit_weights / vg_set_text_features.
+ *   - returns VG_OK (0) or a negative VgStatus; never throws.  vg_last_error gives the text.
+ *   - one handle per device; a handle is not thread-safe (the reference caller is one thread).
+ *   - there is no CPU fallback: every entry point needs an sm_100 device.
+ */
+#ifndef VILGOD_B200_H
+#define VILGOD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VG_API __attribute__((visibility("default")))
+#else
+#define VG_API
+#endif
+
+#define VG_ABI_VERSION 1
+#define VG_MAX_VIEWS 16
+#define VG_VIT_LAYERS 12
+#define VG_VIT_WIDTH 768
+#define VG_VIT_TOKENS 197
+#define VG_VIT_EMBED 512
+#define VG_TILE_ELEMS (196 * 256) /* one 224x224 single-channel image as 196 patch rows of 256 */
+
+typedef enum VgStatus {
+    VG_OK = 0,
+    VG_EINVAL = -1,      /* bad argument / null pointer */
+    VG_ESHAPE = -2,      /* unsupported shape (resolution, views, prompts ...) */
+    VG_EWORKSPACE = -3,  /* workspace too small */
+    VG_EDEGENERATE = -4, /* cluster with no points or zero extent (reference: NaN, mv_utils.py:104) */
+    VG_ECUDA = -5,       /* CUDA error, text in vg_last_error */
+    VG_ESTATE = -6       /* weights / text features not loaded yet */
+} VgStatus;
+
+typedef struct VgHandle VgHandle;
+
+/* rotate_mode: how q = p . rot_mat is rounded (mv_utils.py:199 is a torch bmm whose rounding
+ * depends on the problem size on the reference's CPU path). */
+enum { VG_ROTATE_TORCH_CPU = 0, /* 9N < 400: ((x r0)+(y r1))+(z r2), else fma chain */
+       VG_ROTATE_FUSED = 1, VG_ROTATE_UNFUSED = 2 };
+
+typedef struct VgConfig {
+    int32_t abi_version;      /* VG_ABI_VERSION */
+    int32_t resolution;       /* R, reference 112 (tools/configs/preprocessor/waymo.yaml:79) */
+    int32_t depth;            /* D, reference 8 */
+    int32_t image_size;       /* S, reference 224 (tools/configs/preprocessing.yaml:78) */
+    int32_t num_views;        /* V <= VG_MAX_VIEWS */
+    int32_t rotate_mode;      /* VG_ROTATE_* */
+    double obj_ratio;         /* 0.8  (python scalars: converted to fp32 like torch does) */
+    double depth_bias;        /* 0.2 */
+    double logit_scale;       /* 100.0 (src/utils/clip_utils.py:43) */
+    float rot[VG_MAX_VIEWS][9]; /* rot_mat[v] row-major, q = p . rot  (mv_utils.py:165-166) */
+    float gauss[9];           /* Conv3d weight [3][3] (mv_utils.py:23-27) */
+} VgConfig;
+
+/* Visual tower parameters, fp32 device pointers, reference names and shapes
+ * (clip_model.visual.state_dict()). */
+typedef struct VgVitLayerWeights {
+    const float *ln_1_weight, *ln_1_bias;             /* [768] */
+    const float *attn_in_proj_weight;                 /* [2304,768]  rows [q;k;v] */
+    const float *attn_in_proj_bias;                   /* [2304] */
+    const float *attn_out_proj_weight;                /* [768,768] */
+    const float *attn_out_proj_bias;                  /* [768] */
+    const float *ln_2_weight, *ln_2_bias;             /* [768] */
+    const float *mlp_c_fc_weight, *mlp_c_fc_bias;     /* [3072,768], [3072] */
+    const float *mlp_c_proj_weight, *mlp_c_proj_bias; /* [768,3072], [768] */
+} VgVitLayerWeights;
+
+typedef struct VgVitWeights {
+    const float *conv1_weight;         /* [768,3,16,16], no bias */
+    const float *class_embedding;      /* [768] */
+    const float *positional_embedding; /* [197,768] */
+    const float *ln_pre_weight, *ln_pre_bias;
+    VgVitLayerWeights layers[VG_VIT_LAYERS];
+    const float *ln_post_weight, *ln_post_bias;
+    const float *proj;                 /* [768,512], applied as x @ proj */
+} VgVitWeights;
+
+/* optional stage taps for parity tests (all nullable, device pointers) */
+typedef struct VgProjectDebug {
+    float *d_grid;      /* [B, D, R, R]   scatter-max winners, (z, y, x) order */
+    float *d_densified; /* [B, R-2, R-2]  1 - img/max, (y, x) order */
+} VgProjectDebug;
+
+typedef struct VgVitDebug {
+    int32_t stop_after_layer; /* -1: full; k: stop after resblock k (0..11); -2: after ln_pre */
+    float *d_x;               /* [B,197,768] residual stream at the stop point */
+} VgVitDebug;
+
+VG_API int vg_create(const VgConfig *cfg, VgHandle **out);
+VG_API void vg_destroy(VgHandle *h);
+VG_API const char *vg_last_error(const VgHandle *h);
+VG_API int vg_abi_version(void);
+
+VG_API int vg_load_vit_weights(VgHandle *h, const VgVitWeights *w, void *stream);
+/* d_text: [P,512] fp32 L2-normalised prompt embeddings (device).  class_map: HOST int32 [P] giving
+ * the mapped class id (0..K-1) of each prompt, ids ordered ALPHABETICALLY by mapped class name so
+ * that the vote's tie-break equals np.unique's order (lidar_frame.py:269-283). */
+VG_API int vg_set_text_features(VgHandle *h, const float *d_text, int32_t P, const int32_t *class_map,
+                         int32_t K, void *stream);
+
+/* bytes of scratch vg_encode_score / vg_classify need for up to max_images images per call */
+VG_API size_t vg_workspace_bytes(const VgHandle *h, int64_t max_images);
+
+/* Projection: packed ragged clusters -> B = C*V images, cluster-major / view-minor.
+ *   d_points  [sum N, 3] fp32 (already canonicalised, zero_shot_detector.py:391-393)
+ *   d_offsets [C+1] int32
+ *   d_tiles   [B, 196, 256] bf16, patch-major: tile[b][py*14+px][ky*16+kx] = uint8 pixel value
+ *             floor(img*255) of image row 16*py+ky, column 16*px+kx  (nullable)
+ *   d_u8      [B, 224, 224] uint8, the reference's PIL image, channel 0  (nullable)
+ *   d_status  [C] int32: VG_OK or VG_EDEGENERATE per cluster (nullable) */
+VG_API int vg_project(VgHandle *h, const float *d_points, const int32_t *d_offsets, int32_t C,
+               void *d_tiles, uint8_t *d_u8, int32_t *d_status, const VgProjectDebug *dbg,
+               void *stream);
+
+/* ViT-B/16 + scoring on B images given as patch-major bf16 tiles.
+ *   d_probs [B,P] fp32 softmax(logit_scale * cos)   d_top1 [B] int32 arg-max prompt
+ *   d_feats [B,512] fp32 L2-normalised image embedding (nullable)
+ *   d_logits [B,P] fp32 (nullable) */
+VG_API int vg_encode_score(VgHandle *h, const void *d_tiles, int64_t B, float *d_probs, int32_t *d_top1,
+                    float *d_feats, float *d_logits, void *d_ws, size_t ws_bytes,
+                    const VgVitDebug *dbg, void *stream);
+
+/* Per-cluster view vote on the mapped classes.  d_voted_class [C] int32, d_voted_score [C] fp32 */
+VG_API int vg_vote(VgHandle *h, const float *d_probs, const int32_t *d_top1, int32_t C,
+            int32_t *d_voted_class, float *d_voted_score, void *stream);
+
+/* project -> encode/score -> vote for C clusters, chunked internally to the workspace.
+ * Outputs as above; d_tiles scratch comes out of the workspace. */
+VG_API int vg_classify(VgHandle *h, const float *d_points, const int32_t *d_offsets, int32_t C,
+                float *d_probs, int32_t *d_top1, float *d_feats, int32_t *d_voted_class,
+                float *d_voted_score, int32_t *d_status, void *d_ws, size_t ws_bytes,
+                void *stream);
+
+/* ---- kernel-level test hooks (used by tests/ only; same kernels the entry points launch) ---- */
+enum { VG_EPI_BIAS_BF16 = 0, VG_EPI_BIAS_QGELU_BF16 = 1, VG_EPI_BIAS_RESID_F32 = 2 };
+/* out = epilogue(A[M,K] (bf16, row-major) x W[N,K]^T (bf16, row-major) + bias[N]) */
+VG_API int vg_test_gemm(VgHandle *h, const void *d_a, const void *d_w, const float *d_bias, int64_t M,
+                 int32_t N, int32_t K, int32_t epilogue, void *d_out, void *stream);
+/* qkv [B,197,2304] bf16 (q already scaled) -> out [B,197,768] bf16 */
+VG_API int vg_test_attention(VgHandle *h, const void *d_qkv, int64_t B, void *d_out, void *stream);
+/* x [rows,768] fp32 -> y bf16 [rows,768] = LayerNorm(x) * w + b */
+VG_API int vg_test_layernorm(VgHandle *h, const float *d_x, const float *d_w, const float *d_b,
+                      int64_t rows, void *d_y, void *stream);
+/* number of kernel launches the library has issued on this handle (for bench.py's gpu_launches) */
+VG_API int64_t vg_launch_count(const VgHandle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VILGOD_B200_H */

@@ -156,6 +156,9 @@ int vgo_densify(const float *grid, int R, int D, const float *gauss9, float *img
         /* Conv3d kernel (1,3,3), zero padding (0,1,1), bias 0 */
         for (int i = 0; i < Q; ++i)
             for (int j = 0; j < Q; ++j) {
+                /* row-major tap order, acc = fma(w, p, acc) starting from 0 (zero-padded taps
+                 * leave acc unchanged) -- the order the CUDA kernel uses; the reference's
+                 * cuDNN/oneDNN order is unspecified, hence the 1e-5 contract on this stage */
                 float acc = 0.0f;
                 for (int di = -1; di <= 1; ++di) {
                     int y = i + di;
@@ -163,8 +166,7 @@ int vgo_densify(const float *grid, int R, int D, const float *gauss9, float *img
                     for (int dj = -1; dj <= 1; ++dj) {
                         int x = j + dj;
                         if (x < 0 || x >= Q) continue;
-                        float p = gauss9[(di + 1) * 3 + (dj + 1)] * pool[y * Q + x];
-                        acc = acc + p;
+                        acc = fmaf(gauss9[(di + 1) * 3 + (dj + 1)], pool[y * Q + x], acc);
                     }
                 }
                 conv[i * Q + j] = acc;

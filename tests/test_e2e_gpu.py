@@ -1,0 +1,110 @@
+"""GPU end to end: BASELINE.json configs[0] (one synthetic Waymo-shaped frame, 128 clusters, 6
+views) through vg_classify against the golden run of the UNMODIFIED reference on the same inputs
+and random-init weights, plus a well-separated-prompt variant where top-1 must agree >= 99.5 %."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pipeline as opipe
+from oracle import vit as ovit
+from oracle import vote as ovote
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine6():
+    from vilgod_b200 import weights
+    from vilgod_b200.engine import Engine
+    e = Engine(num_views=6)
+    e.load_vit_weights(weights.random_init_visual_state_dict(1234))
+    yield e
+    e.close()
+
+
+def test_cfg1_frame_against_reference_golden(golden, engine6):
+    g, t = golden["e2e"], golden["tables"]
+    e = engine6
+    e.set_text_features(t["text_features"])
+    out = e.classify(g["points"], g["offsets"])
+    torch.cuda.synchronize()
+    assert int(out["status"].abs().sum()) == 0
+    C, V = 128, 6
+    probs = out["probs"].cpu().numpy().reshape(C * V, 24)
+    ref_logits = g["logits"]
+    ref_probs = torch.from_numpy(ref_logits).softmax(dim=-1).numpy()
+    # stated bf16 tolerance: probabilities within CLIP's own test tolerance (atol 0.01)
+    assert np.abs(probs - ref_probs).max() <= 0.01
+    feats = out["feats"].cpu().numpy().reshape(C * V, 512)
+    cos = (feats * g["feats"].astype(np.float32)).sum(axis=1)
+    assert cos.min() >= 0.9995
+    # top-1: raw agreement is reported, margin-aware agreement is asserted.  With a random-init
+    # text tower all 24 prompts collapse (median top1-top2 margin ~0.04 logit units), so only
+    # images whose reference margin exceeds the stated logit tolerance are decidable.
+    top1 = out["top1"].cpu().numpy().reshape(-1)
+    ref_top1 = ref_logits.argmax(axis=1)
+    srt = np.sort(ref_logits, axis=1)
+    margin = srt[:, -1] - srt[:, -2]
+    clear = margin > 0.06
+    raw = (top1 == ref_top1).mean()
+    aware = (top1[clear] == ref_top1[clear]).mean() if clear.any() else 1.0
+    print(f"cfg1 top-1 agreement raw {raw:.4f}, margin-aware {aware:.4f} on {clear.sum()} images")
+    assert aware >= 0.995
+    assert raw >= 0.80
+
+
+def test_cfg1_frame_well_separated_prompts(golden, engine6):
+    """Same frame and weights, prompt embeddings replaced by well-separated unit vectors (the
+    prompt embeddings are an input of the path): margins >> bf16 noise, so >= 99.5 % top-1 and the
+    4-class voted labels must match the fp32 oracle."""
+    from vilgod_b200 import weights
+    g = golden["e2e"]
+    e = engine6
+    text = weights.synthetic_text_features(24)
+    e.set_text_features(text)
+    C, V = 48, 6
+    off = g["offsets"][:C + 1]
+    pts = g["points"][:off[-1]]
+    out = e.classify(pts, off)
+    ref = opipe.classify(pts, off, V, ovit.make_visual_weights(1234), text.numpy())
+    top1 = out["top1"].cpu().numpy()
+    agree = (top1 == ref["top1"]).mean()
+    srt = np.sort(ref["logits"].reshape(-1, 24), axis=1)
+    print(f"separated prompts: top-1 agreement {agree:.4f}, median margin {np.median(srt[:, -1] - srt[:, -2]):.3f}")
+    assert agree >= 0.995
+    assert np.abs(out["probs"].cpu().numpy() - ref["probs"]).max() <= 0.02
+    names = np.asarray(e.mapped_names)[out["voted_class"].cpu().numpy()]
+    assert (names == ref["voted_name"]).mean() >= 0.97
+    same = names == ref["voted_name"]
+    assert np.abs(out["voted_score"].cpu().numpy()[same] - ref["voted_score"][same]).max() <= 0.02
+
+
+def test_classify_frame_mirror_and_chunking(golden, engine6):
+    """classify_frame (host glue of classification()) on raw clusters, and vg_classify's internal
+    chunking: a small workspace must give the same bits as one big chunk."""
+    from vilgod_b200 import synthetic
+    from vilgod_b200.reference_api import classify_frame
+    e = engine6
+    e.set_text_features(golden["tables"]["text_features"])
+    raw, off, _ = synthetic.make_clusters_raw(20, n_min=10, n_max=500, seed=9)
+    clusters = [raw[off[c]:off[c + 1]] for c in range(20)]
+    res = classify_frame(e, clusters, transform_to_ego=np.eye(4))
+    assert res["class_names"].shape == (20, 6) and res["class_scores"].dtype == np.float32
+    assert set(res["voted_names"]) <= set(e.mapped_names)
+    from vilgod_b200 import canonicalise
+    packed = canonicalise.canonicalise_packed(raw, off, np.eye(4))
+    full = e.classify(packed, off)
+    probs_full = full["probs"].clone()
+    import ctypes as C
+    need = int(e.lib.vg_workspace_bytes(e._h, 12))          # room for 2 clusters x 6 views
+    e._ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    ws_small = e._ws
+    orig = e.workspace
+    e.workspace = lambda n: ws_small
+    try:
+        small = e.classify(packed, off)
+    finally:
+        e.workspace = orig
+        e._ws = None
+    assert torch.equal(small["probs"], probs_full)
+    assert torch.equal(small["voted_class"], full["voted_class"])

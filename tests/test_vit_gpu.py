@@ -1,0 +1,178 @@
+"""GPU parity of the ViT kernels (tcgen05 GEMM, fused attention, LayerNorm, head, vote) through the
+C ABI.  Kernel-level checks use a plain torch fp32 reference of the same op on bf16-rounded
+operands; tower-level checks use the oracle (oracle/vit.py) and the golden vectors from the
+reference.  Tolerances are stated next to each assert."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vit as ovit
+from oracle import vote as ovote
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from vilgod_b200.engine import Engine
+    e = Engine(num_views=6)
+    yield e
+    e.close()
+
+
+def _loaded_engine(golden, tag):
+    from vilgod_b200 import weights
+    from vilgod_b200.engine import Engine
+    e = Engine(num_views=6)
+    sd = weights.random_init_visual_state_dict(1234)
+    if tag == "ln":
+        sd = weights.perturb_layernorms(sd)
+    e.load_vit_weights(sd)
+    e.set_text_features(golden["tables"]["text_features"])
+    return e
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 768, 256), (197 * 3, 2304, 768),
+                                   (1000, 3072, 768), (197 * 5 + 3, 768, 3072), (1, 256, 64),
+                                   (148 * 128 * 2 + 77, 768, 768)])
+@pytest.mark.parametrize("epi", [0, 1, 2])
+def test_tcgen05_gemm_against_torch(eng, M, N, K, epi):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N + K + epi)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * (K ** -0.5)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = a.float() @ w.float().T + bias
+    if epi == 0:
+        out = eng.test_gemm(a, w, bias, 0).float()
+        tol = 2 ** -8 * ref.abs().max().item() + 1e-3          # one bf16 rounding of the output
+    elif epi == 1:
+        ref = ref * torch.sigmoid(1.702 * ref)
+        out = eng.test_gemm(a, w, bias, 1).float()
+        tol = 2 ** -8 * ref.abs().max().item() + 2e-3
+    else:
+        x0 = torch.randn(M, N, device="cuda", generator=g)
+        ref = ref + x0
+        out = eng.test_gemm(a, w, bias, 2, out=x0.clone())
+        tol = 2e-4 * max(1.0, K / 768)                          # fp32 accumulation order only
+    err = (out - ref).abs().max().item()
+    assert err <= tol, (err, tol)
+
+
+@pytest.mark.parametrize("B", [1, 3, 16])
+def test_fused_attention_against_torch(eng, B):
+    g = torch.Generator(device="cuda").manual_seed(B)
+    qkv = (torch.randn(B, 197, 2304, device="cuda", generator=g)).bfloat16()
+    qkv[:, :, :768] *= 0.35    # keep logits in a realistic range (q arrives pre-scaled by 1/8)
+    out = eng.test_attention(qkv).float()
+    q, k, v = qkv.float().split(768, dim=-1)
+    q = q.view(B, 197, 12, 64).transpose(1, 2)
+    k = k.view(B, 197, 12, 64).transpose(1, 2)
+    v = v.view(B, 197, 12, 64).transpose(1, 2)
+    ref = (torch.softmax(q @ k.transpose(-1, -2), dim=-1) @ v).transpose(1, 2).reshape(B, 197, 768)
+    # P is rounded to bf16 before P.V and the output is bf16: 2^-8 relative each
+    assert (out - ref).abs().max().item() <= 2e-2
+    assert (out - ref).abs().mean().item() <= 2e-3
+
+
+def test_layernorm_against_torch(eng):
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(197 * 4 + 5, 768, device="cuda", generator=g) * 3 + 0.7
+    w = torch.randn(768, device="cuda", generator=g)
+    b = torch.randn(768, device="cuda", generator=g)
+    ref = torch.nn.functional.layer_norm(x, (768,), w, b, 1e-5)
+    out = eng.test_layernorm(x, w, b).float()
+    assert (out - ref).abs().max().item() <= 2 ** -8 * ref.abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize("tag", ["plain", "ln"])
+def test_tower_stages_against_reference_golden(golden, tag):
+    """8 golden depth images: residual stream after ln_pre / block 0 / block 11 (rows 0..2) and the
+    final embedding against the reference's fp32 run.  bf16 GEMM operands, fp32 everything else."""
+    from vilgod_b200.engine import u8_to_tiles
+    g = golden["vit"]
+    e = _loaded_engine(golden, tag)
+    try:
+        tiles = u8_to_tiles(torch.from_numpy(g["u8"]).cuda())
+        x = e.encode_score(tiles, stop_after_layer=-2)["x"][:, :3].cpu().numpy()
+        # patch-embed with bf16 weights: K=256 products of integers <=255 with 2^-9 relative weight
+        # error, then LayerNorm (unit variance output)
+        assert np.abs(x - g[f"{tag}_ln_pre"]).max() <= 3e-2
+        x = e.encode_score(tiles, stop_after_layer=0)["x"][:, :3].cpu().numpy()
+        assert np.abs(x - g[f"{tag}_block0"]).max() <= 6e-2
+        x = e.encode_score(tiles, stop_after_layer=11)["x"][:, :3].cpu().numpy()
+        ref = g[f"{tag}_block11"]
+        assert np.abs(x - ref).max() <= 0.03 * np.abs(ref).max() + 0.1
+        res = e.encode_score(tiles, want_logits=True)
+        f_ref = g[f"{tag}_feats"] / np.linalg.norm(g[f"{tag}_feats"], axis=1, keepdims=True)
+        cos = (res["feats"].cpu().numpy() * f_ref).sum(axis=1)
+        assert cos.min() >= 0.9995, cos.min()
+        # stated bf16 tolerance on logits (100 * cos units): 0.15 raw, 0.06 after removing the
+        # per-image offset that soft-max ignores
+        d = res["logits"].cpu().numpy() - g[f"{tag}_logits"]
+        assert np.abs(d).max() <= 0.15, np.abs(d).max()
+        assert np.abs(d - d.mean(axis=1, keepdims=True)).max() <= 0.06
+        assert np.abs(res["probs"].cpu().numpy() - g[f"{tag}_probs"]).max() <= 0.01
+    finally:
+        e.close()
+
+
+def test_head_matches_oracle_given_same_residual(golden):
+    """Isolate the fused head: feed the kernel's own block-11 residual stream to the oracle's
+    ln_post / proj / normalise / score and compare at fp32 tolerance."""
+    from vilgod_b200.engine import u8_to_tiles
+    g = golden["vit"]
+    e = _loaded_engine(golden, "ln")
+    try:
+        w = ovit.perturb_layernorms(ovit.make_visual_weights(1234))
+        tiles = u8_to_tiles(torch.from_numpy(g["u8"]).cuda())
+        x = e.encode_score(tiles, stop_after_layer=11)["x"].cpu()
+        res = e.encode_score(tiles, want_logits=True)
+        y = torch.nn.functional.layer_norm(x[:, 0], (768,), w["ln_post.weight"], w["ln_post.bias"], 1e-5)
+        probs, logits, fn = ovit.score(y @ w["proj"], golden["tables"]["text_features"])
+        assert (res["feats"].cpu() - fn).abs().max().item() <= 2e-5
+        assert (res["logits"].cpu() - logits).abs().max().item() <= 2e-3
+        assert (res["probs"].cpu() - probs).abs().max().item() <= 1e-4
+        margin = torch.sort(logits, dim=1).values
+        clear = (margin[:, -1] - margin[:, -2]) > 5e-3
+        assert torch.equal(res["top1"].cpu()[clear].long(), logits.argmax(dim=1)[clear])
+    finally:
+        e.close()
+
+
+@pytest.mark.parametrize("V", [4, 6, 10])
+def test_gpu_vote_matches_reference(golden, V):
+    from vilgod_b200.engine import CLASS_LIST, Engine
+    g = golden["vote"]
+    e = Engine(num_views=V)
+    try:
+        e.set_text_features(torch.randn(24, 512))
+        idx, scores = g[f"idx{V}"], g[f"scores{V}"]
+        C = idx.shape[0]
+        probs = torch.zeros(C * V, 24)
+        probs[torch.arange(C * V), torch.from_numpy(idx.reshape(-1)).long()] = torch.from_numpy(scores.reshape(-1))
+        vc, vs = e.vote(probs.cuda(), torch.from_numpy(idx.reshape(-1)).int().cuda())
+        names = np.asarray(e.mapped_names)[vc.cpu().numpy()]
+        assert np.array_equal(names, g[f"voted_name{V}"])
+        assert np.array_equal(vs.cpu().numpy(), g[f"voted_score{V}"])
+    finally:
+        e.close()
+
+
+def test_error_paths(golden):
+    from vilgod_b200 import _lib
+    from vilgod_b200.engine import Engine, VilgodError
+    e = Engine(num_views=4)
+    try:
+        tiles = torch.zeros(2, 196, 256, dtype=torch.bfloat16, device="cuda")
+        e.num_prompts = 24
+        with pytest.raises(VilgodError) as ei:
+            e.encode_score(tiles)
+        assert ei.value.code == _lib.VG_ESTATE
+        with pytest.raises(ValueError):
+            e.set_text_features(torch.randn(24, 100))
+        with pytest.raises(KeyError):
+            e.load_vit_weights({"conv1.weight": torch.zeros(768, 3, 16, 16)})
+    finally:
+        e.close()
+    with pytest.raises(VilgodError):
+        Engine(num_views=4, resolution=224)

@@ -1,0 +1,112 @@
+// Shared declarations of the vilgod_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/vilgod_b200.h"
+
+namespace vg {
+
+constexpr int kWidth = VG_VIT_WIDTH;     // 768
+constexpr int kTokens = VG_VIT_TOKENS;   // 197
+constexpr int kPatches = 196;
+constexpr int kHeads = 12;
+constexpr int kHeadDim = 64;
+constexpr int kLayers = VG_VIT_LAYERS;
+constexpr int kMlp = 3072;
+constexpr int kEmbed = VG_VIT_EMBED;     // 512
+constexpr int kPatchK = 256;             // folded patch-embed K (3 identical channels summed)
+constexpr int kMaxPrompts = 64;
+
+struct LayerDev {
+    __nv_bfloat16 *w_qkv, *w_out, *w_fc, *w_proj;   // [N,K] row-major bf16
+    float *b_qkv, *b_out, *b_fc, *b_proj;           // fp32
+    float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
+};
+
+struct VitDev {
+    __nv_bfloat16 *w_patch;   // [768,256] folded patch embedding
+    float *patch_bias_pos;    // [197,768]: row 0 = cls + pos[0]; row 1+p = b_eff + pos[1+p]
+    float *ln_pre_w, *ln_pre_b, *ln_post_w, *ln_post_b;
+    float *proj;              // [768,512] fp32
+    LayerDev layer[kLayers];
+    bool loaded = false;
+};
+
+}  // namespace vg
+
+struct VgHandle {
+    VgConfig cfg;
+    int device = 0;
+    int num_sms = 148;
+    char err[512];
+    int64_t launches = 0;
+    vg::VitDev vit;
+    float *d_text = nullptr;        // [P,512]
+    int32_t *d_class_map = nullptr; // [P]
+    int32_t num_prompts = 0, num_classes = 0;
+    void *arena = nullptr;          // one device allocation holding all converted weights
+    size_t arena_bytes = 0;
+    void *tma_encode = nullptr;     // cuTensorMapEncodeTiled entry point
+};
+
+#define VG_SET_ERR(h, ...)                                   \
+    do {                                                     \
+        if (h) snprintf((h)->err, sizeof((h)->err), __VA_ARGS__); \
+    } while (0)
+
+#define VG_CUDA_CHECK(h, expr)                                                        \
+    do {                                                                              \
+        cudaError_t _e = (expr);                                                      \
+        if (_e != cudaSuccess) {                                                      \
+            VG_SET_ERR(h, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                       __LINE__);                                                     \
+            return VG_ECUDA;                                                          \
+        }                                                                             \
+    } while (0)
+
+#define VG_LAUNCH_CHECK(h)                                   \
+    do {                                                     \
+        (h)->launches++;                                     \
+        VG_CUDA_CHECK(h, cudaGetLastError());                \
+    } while (0)
+
+// kernel launchers implemented in the .cu files ------------------------------------------------
+namespace vg {
+
+int launch_projection(VgHandle *h, const float *d_points, const int32_t *d_offsets, int32_t C,
+                      __nv_bfloat16 *d_tiles, uint8_t *d_u8, int32_t *d_status,
+                      const VgProjectDebug *dbg, cudaStream_t st);
+
+// D = epilogue(A[M,K] * W[N,K]^T + bias).  a_row_map: optional remap used by the patch-embed.
+struct GemmArgs {
+    const __nv_bfloat16 *a;   // [M,K]
+    const __nv_bfloat16 *w;   // [N,K]
+    const float *bias;        // [N] (or [197,N] table for the patch-embed epilogue)
+    void *out;                // bf16 [M,N] or fp32 [M,N] (resid: in/out)
+    int64_t M;
+    int32_t N, K;
+    int32_t epilogue;         // VG_EPI_* or kEpiPatch
+};
+constexpr int kEpiPatch = 3;  // out fp32 x[img*197 + 1 + p][n] = acc + table[1+p][n]
+int launch_gemm(VgHandle *h, const GemmArgs &g, cudaStream_t st);
+
+int launch_attention(VgHandle *h, const __nv_bfloat16 *qkv, int64_t B, __nv_bfloat16 *out,
+                     cudaStream_t st);
+int launch_layernorm_bf16(VgHandle *h, const float *x, const float *w, const float *b,
+                          int64_t rows, __nv_bfloat16 *y, cudaStream_t st);
+// x[img,0,:] = table[0]; then x = LN(x) in place (ln_pre) over all B*197 rows
+int launch_ln_pre(VgHandle *h, float *x, int64_t B, cudaStream_t st);
+// ln_post on CLS rows -> proj -> L2 norm -> logits -> softmax -> argmax
+int launch_head(VgHandle *h, const float *x, int64_t B, float *probs, int32_t *top1, float *feats,
+                float *logits, cudaStream_t st);
+int launch_vote(VgHandle *h, const float *probs, const int32_t *top1, int32_t C,
+                int32_t *voted_class, float *voted_score, cudaStream_t st);
+int convert_weights(VgHandle *h, const VgVitWeights *w, cudaStream_t st);
+
+}  // namespace vg

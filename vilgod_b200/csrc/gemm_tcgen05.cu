@@ -1,0 +1,306 @@
+// Persistent, warp-specialised bf16 GEMM on the 5th-generation tensor cores (tcgen05 + TMEM),
+// operands staged by TMA -- the linear layers of the CLIP ViT-B/16 visual tower:
+//   patch embedding (folded conv1)      third_party/CLIP/clip/model.py:224-229
+//   attention in-proj / out-proj        third_party/CLIP/clip/model.py:187 (nn.MultiheadAttention)
+//   MLP c_fc (+QuickGELU) / c_proj      third_party/CLIP/clip/model.py:177-181,191
+//
+//   D[M,N] = epilogue( A[M,K] . W[N,K]^T + bias[N] ),  A / W bf16 row-major (both K-major), fp32
+//   accumulation in tensor memory.
+//
+// CTA = 6 warps on one SM (one CTA per SM, grid = min(#tiles, #SMs), static round-robin tiles):
+//   warp 0      TMA producer : 4-stage ring of {A 128x64, W 256x64} bf16 tiles, SWIZZLE_128B
+//   warp 1      MMA issuer   : tcgen05.mma.cta_group::1.kind::f16, UMMA 128x256x16, one elected lane;
+//                              owns the 512-column TMEM allocation (2 accumulator stages x 256)
+//   warps 2..5  epilogue     : tcgen05.ld 32x32b -> registers -> bias / QuickGELU / residual ->
+//                              global; overlaps the next tile's main loop through the second
+//                              accumulator stage
+// Synchronisation is mbarrier-only: full/empty per smem stage (TMA tx-count / tcgen05.commit) and
+// full/empty per accumulator stage (tcgen05.commit / 128 epilogue arrivals).
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace vg {
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64, UK = 16;
+constexpr int STAGES = 4;
+constexpr int ACC_STAGES = 2;
+constexpr int A_BYTES = BM * BK * 2;   // 16 KiB
+constexpr int B_BYTES = BN * BK * 2;   // 32 KiB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int GEMM_THREADS = 192;
+constexpr int EPI_THREADS = 128;
+constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct GemmParams {
+    const float *bias;
+    void *out;
+    int64_t M;
+    int32_t N, K;
+};
+
+__device__ __forceinline__ float quick_gelu(float v)
+{
+    // x * sigmoid(1.702 x)   (model.py:166-168)
+    return __fdividef(v, 1.0f + __expf(-1.702f * v));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b)
+{
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&t);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+            const GemmParams p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment
+    unsigned char *smem = reinterpret_cast<unsigned char *>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * STAGE_BYTES);
+    uint64_t *full_bar = bars;                               // [STAGES]
+    uint64_t *empty_bar = bars + STAGES;                     // [STAGES]
+    uint64_t *tmem_full = bars + 2 * STAGES;                 // [ACC_STAGES]
+    uint64_t *tmem_empty = bars + 2 * STAGES + ACC_STAGES;   // [ACC_STAGES]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 2 * ACC_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles = (int)((p.M + BM - 1) / BM);
+    const int n_tiles = p.N / BN;
+    const int num_tiles = m_tiles * n_tiles;
+    const int num_kb = p.K / BK;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tma_a);
+        ptx::prefetch_tensormap(&tma_b);
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < ACC_STAGES; ++s) {
+            ptx::mbar_init(&tmem_full[s], 1);
+            ptx::mbar_init(&tmem_empty[s], EPI_THREADS);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, ACC_STAGES * BN);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    unsigned char *sa = smem + (size_t)stage * STAGE_BYTES;
+                    unsigned char *sb = sa + A_BYTES;
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                    ptx::tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
+                    ptx::tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(BM, BN);
+            int stage = 0, as = 0;
+            uint32_t phase = 0, aphase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                ptx::mbar_wait(&tmem_empty[as], aphase ^ 1u);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * STAGE_BYTES);
+                    const uint64_t da = ptx::make_kmajor_sw128_desc(sa);
+                    const uint64_t db = ptx::make_kmajor_sw128_desc(sa + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UK; ++k) {
+                        // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle atom:
+                        // +2 in the 16-byte units of the descriptor's start-address field
+                        ptx::mma_f16_ss(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                        (uint32_t)((kb | k) != 0));
+                    }
+                    ptx::tc_commit(&empty_bar[stage]);   // frees the smem stage when the MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                ptx::tc_commit(&tmem_full[as]);          // accumulator ready for the epilogue
+                if (++as == ACC_STAGES) { as = 0; aphase ^= 1u; }
+            }
+        }
+    } else {
+        // ================= epilogue warps =================
+        const int lane_base = (warp & 3) * 32;   // TMEM lanes this warp may touch
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+            ptx::mbar_wait(&tmem_full[as], aphase);
+            ptx::tc_fence_after();
+            const int64_t row = (int64_t)m_blk * BM + lane_base + lane;
+            const bool row_ok = row < p.M;
+            int64_t orow = row;
+            const float *brow = p.bias;
+            if (EPI == kEpiPatch) {
+                // A row = img*196 + patch  ->  residual-stream row img*197 + 1 + patch;
+                // "bias" is the [197,768] table b_eff + positional embedding
+                const int64_t img = row / kPatches;
+                const int patch = (int)(row - img * kPatches);
+                orow = img * kTokens + 1 + patch;
+                brow = p.bias + (size_t)(1 + patch) * p.N;
+            }
+#pragma unroll 1
+            for (int chunk = 0; chunk < BN / 32; ++chunk) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) +
+                                       (uint32_t)(as * BN + chunk * 32);
+                ptx::tmem_ld_32x32b_x32(taddr, r);
+                ptx::tmem_ld_wait();
+                const int n0 = n_blk * BN + chunk * 32;
+                if (row_ok) {
+                    const float4 *b4 = reinterpret_cast<const float4 *>(brow + n0);
+                    if (EPI == VG_EPI_BIAS_BF16 || EPI == VG_EPI_BIAS_QGELU_BF16) {
+                        uint4 *dst = reinterpret_cast<uint4 *>(
+                            reinterpret_cast<__nv_bfloat16 *>(p.out) + orow * p.N + n0);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float v[8];
+                            const float4 ba = __ldg(b4 + 2 * q), bb = __ldg(b4 + 2 * q + 1);
+                            const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                v[j] = __uint_as_float(r[8 * q + j]) + bv[j];
+                                if (EPI == VG_EPI_BIAS_QGELU_BF16) v[j] = quick_gelu(v[j]);
+                            }
+                            dst[q] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+                                                pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                        }
+                    } else {
+                        float4 *dst =
+                            reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + orow * p.N + n0);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 bv = __ldg(b4 + q);
+                            float4 o;
+                            o.x = __uint_as_float(r[4 * q + 0]) + bv.x;
+                            o.y = __uint_as_float(r[4 * q + 1]) + bv.y;
+                            o.z = __uint_as_float(r[4 * q + 2]) + bv.z;
+                            o.w = __uint_as_float(r[4 * q + 3]) + bv.w;
+                            if (EPI == VG_EPI_BIAS_RESID_F32) {   // x += attn / mlp branch
+                                const float4 x = dst[q];
+                                o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
+                            }
+                            dst[q] = o;
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&tmem_empty[as]);
+            if (++as == ACC_STAGES) { as = 0; aphase ^= 1u; }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, ACC_STAGES * BN);
+    }
+}
+
+int make_tmap_2d(VgHandle *h, CUtensorMap *map, const void *ptr, uint64_t rows, uint64_t cols,
+                 uint32_t box_rows, uint32_t box_cols)
+{
+    auto encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(h->tma_encode);
+    if (!encode) {
+        VG_SET_ERR(h, "cuTensorMapEncodeTiled entry point unavailable");
+        return VG_ECUDA;
+    }
+    const cuuint64_t gdim[2] = {cols, rows};
+    const cuuint64_t gstride[1] = {cols * sizeof(__nv_bfloat16)};
+    const cuuint32_t box[2] = {box_cols, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), gdim,
+                        gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        VG_SET_ERR(h, "cuTensorMapEncodeTiled failed (CUresult %d) rows=%llu cols=%llu", (int)r,
+                   (unsigned long long)rows, (unsigned long long)cols);
+        return VG_ECUDA;
+    }
+    return VG_OK;
+}
+
+template <int EPI>
+int launch_gemm_t(VgHandle *h, const GemmArgs &g, cudaStream_t st)
+{
+    CUtensorMap ta, tb;
+    int rc = make_tmap_2d(h, &ta, g.a, (uint64_t)g.M, (uint64_t)g.K, BM, BK);
+    if (rc) return rc;
+    rc = make_tmap_2d(h, &tb, g.w, (uint64_t)g.N, (uint64_t)g.K, BN, BK);
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VG_CUDA_CHECK(h, cudaFuncSetAttribute(gemm_kernel<EPI>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)GEMM_SMEM));
+        attr_set = true;
+    }
+    GemmParams p;
+    p.bias = g.bias;
+    p.out = g.out;
+    p.M = g.M;
+    p.N = g.N;
+    p.K = g.K;
+    const int64_t tiles = ((g.M + BM - 1) / BM) * (g.N / BN);
+    const int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+    gemm_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ta, tb, p);
+    VG_LAUNCH_CHECK(h);
+    return VG_OK;
+}
+
+}  // namespace
+
+int launch_gemm(VgHandle *h, const GemmArgs &g, cudaStream_t st)
+{
+    if (g.M <= 0) return VG_OK;
+    if (g.N % BN != 0 || g.K % BK != 0 || g.K <= 0) {
+        VG_SET_ERR(h, "gemm: N must be a multiple of %d and K of %d (got N=%d K=%d)", BN, BK, g.N,
+                   g.K);
+        return VG_ESHAPE;
+    }
+    if ((reinterpret_cast<uintptr_t>(g.a) | reinterpret_cast<uintptr_t>(g.w) |
+         reinterpret_cast<uintptr_t>(g.out)) & 15) {
+        VG_SET_ERR(h, "gemm: operands must be 16-byte aligned");
+        return VG_EINVAL;
+    }
+    switch (g.epilogue) {
+        case VG_EPI_BIAS_BF16: return launch_gemm_t<VG_EPI_BIAS_BF16>(h, g, st);
+        case VG_EPI_BIAS_QGELU_BF16: return launch_gemm_t<VG_EPI_BIAS_QGELU_BF16>(h, g, st);
+        case VG_EPI_BIAS_RESID_F32: return launch_gemm_t<VG_EPI_BIAS_RESID_F32>(h, g, st);
+        case kEpiPatch: return launch_gemm_t<kEpiPatch>(h, g, st);
+    }
+    VG_SET_ERR(h, "gemm: unknown epilogue %d", g.epilogue);
+    return VG_EINVAL;
+}
+
+}  // namespace vg

@@ -1,0 +1,484 @@
+// Multi-view depth projection of packed ragged point clusters -- one fused sm_100a kernel.
+//
+// Replaces, for one (cluster, view) per CTA, everything between the canonicalised cluster and the
+// CLIP patch embedding in the reference:
+//   rotate                        src/utils/mv_utils.py:173-201  (point_transform, torch bmm)
+//   normalise / ceil / clip       src/utils/mv_utils.py:99-118   (points2grid part 1)
+//   3-D grid scatter-max          src/utils/mv_utils.py:120-127  (torch_scatter reduce="max")
+//   5x5 max-pool, 3x3 Gaussian,   src/utils/mv_utils.py:30-37    (GridToImage.forward)
+//   depth max, /max, 1-x
+//   bilinear 110->224, uint8      src/vilgod/zero_shot_detector.py:405-409
+//   ToTensor / Normalize          third_party/CLIP/clip/clip.py:79-86 (folded into the patch-embed
+//                                 weights; the kernel emits the integer pixel 0..255 as bf16)
+//
+// Data flow: points are read from HBM (L2 for views > 0), every intermediate (one depth slice of
+// the grid, the running depth-max image, the horizontally interpolated rows) lives in shared
+// memory, and the only HBM writes are the patch-major bf16 tile (100,352 B per image) and, on
+// request, the uint8 image.  Algorithmic bytes per cluster: 12 N + V * 224*224*2.
+//
+// Numerics contract (tests/test_projection_gpu.py): occupancy masks and scatter winners bit-exact
+// against the oracle; every fp32 operation up to the scatter is a single IEEE-rounded operation in
+// the reference's order (explicit __f*_rn intrinsics: no FMA contraction), the bilinear stage uses
+// exactly the FMA pattern torch-CPU executes, the Gaussian uses a row-major FMA chain (the
+// reference's conv order is unspecified; 1e-5 contract).
+#include "common.cuh"
+
+namespace vg {
+namespace {
+
+constexpr int R = 112;          // grid resolution
+constexpr int D = 8;            // depth slices
+constexpr int S = 224;          // output image size
+constexpr int Q = R - 2;        // densified image size (110)
+constexpr int NT = 512;         // threads per CTA
+constexpr int NW = NT / 32;     // 16 warps
+constexpr int ROWS_PER_WARP = R / NW;  // 7
+constexpr int HI_ROWS = 56;     // source rows whose horizontal interpolation fits the grid buffer
+
+struct ProjParams {
+    const float *points;
+    const int32_t *offsets;
+    int32_t C, V;
+    float rot[VG_MAX_VIEWS * 9];
+    float gauss[9];
+    float obj_ratio, depth_bias, one_plus_bias;
+    int32_t rotate_mode;
+    __nv_bfloat16 *tiles;
+    uint8_t *u8;
+    int32_t *status;
+    float *dbg_grid;
+    float *dbg_dens;
+};
+
+struct Smem {
+    float G[R * R];        // one depth slice of the grid / pooled slice / HI rows (56 x 224)
+    float IMG[R * R];      // running max over depth of the smoothed slices, row stride R
+    float red[6 * NW];
+    float norm[4];         // pcent xyz, prange
+    float mx;
+    unsigned mask;         // occupied depth slices
+    int degenerate;
+};
+
+__device__ __forceinline__ void rotate_point(const float *__restrict__ p, const float *rm,
+                                             bool fused, float &qx, float &qy, float &qz)
+{
+    const float x = p[0], y = p[1], z = p[2];
+    if (fused) {   // BLAS sgemm micro-kernel: fma(z, r2, fma(y, r1, x*r0))
+        qx = __fmaf_rn(z, rm[6], __fmaf_rn(y, rm[3], __fmul_rn(x, rm[0])));
+        qy = __fmaf_rn(z, rm[7], __fmaf_rn(y, rm[4], __fmul_rn(x, rm[1])));
+        qz = __fmaf_rn(z, rm[8], __fmaf_rn(y, rm[5], __fmul_rn(x, rm[2])));
+    } else {       // torch's naive bmm loop: ((x*r0) + (y*r1)) + (z*r2)
+        qx = __fadd_rn(__fadd_rn(__fmul_rn(x, rm[0]), __fmul_rn(y, rm[3])), __fmul_rn(z, rm[6]));
+        qy = __fadd_rn(__fadd_rn(__fmul_rn(x, rm[1]), __fmul_rn(y, rm[4])), __fmul_rn(z, rm[7]));
+        qz = __fadd_rn(__fadd_rn(__fmul_rn(x, rm[2]), __fmul_rn(y, rm[5])), __fmul_rn(z, rm[8]));
+    }
+}
+
+// mv_utils.py:101-118, one rounded op per operator
+__device__ __forceinline__ void quantise(float qx, float qy, float qz, const float *nm,
+                                         const ProjParams &P, int &cell, int &zi, float &val)
+{
+    const float pr = nm[3];
+    float ux = __fmul_rn(__fdiv_rn(__fsub_rn(qx, nm[0]), pr), 2.0f);
+    float uy = __fmul_rn(__fdiv_rn(__fsub_rn(qy, nm[1]), pr), 2.0f);
+    float uz = __fmul_rn(__fdiv_rn(__fsub_rn(qz, nm[2]), pr), 2.0f);
+    ux = __fmul_rn(ux, P.obj_ratio);
+    uy = __fmul_rn(uy, P.obj_ratio);
+    const float fx = __fmul_rn(__fmul_rn(__fadd_rn(ux, 1.0f), 0.5f), (float)R);
+    const float fy = __fmul_rn(__fmul_rn(__fadd_rn(uy, 1.0f), 0.5f), (float)R);
+    float fz = __fadd_rn(__fmul_rn(__fadd_rn(uz, 1.0f), 0.5f), P.depth_bias);
+    fz = __fmul_rn(__fdiv_rn(fz, P.one_plus_bias), (float)(D - 2));
+    const float X = fminf(fmaxf(ceilf(fx), 1.0f), (float)(R - 2));
+    const float Y = fminf(fmaxf(ceilf(fy), 1.0f), (float)(R - 2));
+    zi = (int)ceilf(fz);
+    val = fminf(fmaxf(fz, 1.0f), (float)(D - 2));
+    cell = (int)Y * R + (int)X;
+}
+
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ float4 max4(float4 a, float4 b)
+{
+    return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+
+// bilinear source index / weights, torch area_pixel_compute_source_index(align_corners=True)
+__device__ __forceinline__ void lin_idx(int dst, int &i0, float &l0, float &l1)
+{
+    const float scale = __fdiv_rn((float)(Q - 1), (float)(S - 1));
+    const float src = __fmul_rn(scale, (float)dst);
+    int a = (int)floorf(src);
+    a = min(a, Q - 1);
+    float lam = __fsub_rn(src, (float)a);
+    lam = fminf(fmaxf(lam, 0.0f), 1.0f);
+    i0 = a;
+    l1 = lam;
+    l0 = __fsub_rn(1.0f, lam);
+}
+
+__global__ void __launch_bounds__(NT, 2) projection_kernel(const ProjParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x;
+    const int c = b / P.V, v = b - c * P.V;
+    const int beg = P.offsets[c];
+    const int n = P.offsets[c + 1] - beg;
+    const float *__restrict__ pts = P.points + 3 * (size_t)beg;
+    const float *rm = P.rot + 9 * v;
+    const bool fused = P.rotate_mode == VG_ROTATE_FUSED ||
+                       (P.rotate_mode == VG_ROTATE_TORCH_CPU && 9 * (long long)n >= 400);
+
+    // ---- phase 1: per-axis min / max of the rotated points --------------------------------------
+    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY;
+    float mn0 = INFINITY, mn1 = INFINITY, mn2 = INFINITY;
+    bool finite = true;
+    for (int i = tid; i < n; i += NT) {
+        float qx, qy, qz;
+        rotate_point(pts + 3 * i, rm, fused, qx, qy, qz);
+        finite = finite && isfinite(qx) && isfinite(qy) && isfinite(qz);
+        mx0 = fmaxf(mx0, qx); mx1 = fmaxf(mx1, qy); mx2 = fmaxf(mx2, qz);
+        mn0 = fminf(mn0, qx); mn1 = fminf(mn1, qy); mn2 = fminf(mn2, qz);
+    }
+    mx0 = warp_max(mx0); mx1 = warp_max(mx1); mx2 = warp_max(mx2);
+    mn0 = warp_min(mn0); mn1 = warp_min(mn1); mn2 = warp_min(mn2);
+    const bool all_finite = __all_sync(0xffffffffu, finite);
+    if (tid == 0) { sm.mask = 0u; sm.degenerate = 0; }
+    __syncthreads();
+    if (lane == 0) {
+        sm.red[warp] = mx0; sm.red[NW + warp] = mx1; sm.red[2 * NW + warp] = mx2;
+        sm.red[3 * NW + warp] = mn0; sm.red[4 * NW + warp] = mn1; sm.red[5 * NW + warp] = mn2;
+        if (!all_finite) sm.degenerate = 1;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float a[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            float t = lane < NW ? sm.red[k * NW + lane] : (k < 3 ? -INFINITY : INFINITY);
+            a[k] = k < 3 ? warp_max(t) : warp_min(t);
+        }
+        if (lane == 0) {
+            sm.norm[0] = __fmul_rn(__fadd_rn(a[0], a[3]), 0.5f);
+            sm.norm[1] = __fmul_rn(__fadd_rn(a[1], a[4]), 0.5f);
+            sm.norm[2] = __fmul_rn(__fadd_rn(a[2], a[5]), 0.5f);
+            const float pr = fmaxf(fmaxf(__fsub_rn(a[0], a[3]), __fsub_rn(a[1], a[4])),
+                                   __fsub_rn(a[2], a[5]));
+            sm.norm[3] = pr;
+            if (n <= 0 || !(pr > 0.0f) || !isfinite(pr)) sm.degenerate = 1;
+        }
+    }
+    __syncthreads();
+    if (sm.degenerate) {   // defined behaviour where the reference yields NaN: zero tile + status
+        if (P.tiles) {
+            uint4 *t = reinterpret_cast<uint4 *>(P.tiles + (size_t)b * VG_TILE_ELEMS);
+            for (int i = tid; i < VG_TILE_ELEMS / 8; i += NT) t[i] = make_uint4(0, 0, 0, 0);
+        }
+        if (P.u8) {
+            uint4 *t = reinterpret_cast<uint4 *>(P.u8 + (size_t)b * S * S);
+            for (int i = tid; i < S * S / 16; i += NT) t[i] = make_uint4(0, 0, 0, 0);
+        }
+        if (P.status && v == 0 && tid == 0) P.status[c] = VG_EDEGENERATE;
+        return;
+    }
+    if (P.status && v == 0 && tid == 0) P.status[c] = VG_OK;
+    const float nm[4] = {sm.norm[0], sm.norm[1], sm.norm[2], sm.norm[3]};
+
+    // ---- phase 2: which depth slices are occupied ------------------------------------------------
+    {
+        unsigned m = 0u;
+        for (int i = tid; i < n; i += NT) {
+            float qx, qy, qz, val; int cell, zi;
+            rotate_point(pts + 3 * i, rm, fused, qx, qy, qz);
+            quantise(qx, qy, qz, nm, P, cell, zi, val);
+            m |= 1u << (zi & 31);
+        }
+        m = __reduce_or_sync(0xffffffffu, m);
+        if (lane == 0 && m) atomicOr(&sm.mask, m);
+    }
+    // IMG starts at 0 == max over the empty slices (their smoothed image is identically 0)
+    for (int i = tid; i < R * R / 4; i += NT)
+        reinterpret_cast<float4 *>(sm.IMG)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    const unsigned mask = sm.mask & ((1u << D) - 1u);
+
+    float w[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) w[k] = P.gauss[k];
+
+    // ---- phase 3: per occupied slice: scatter-max, 5x5 max-pool, 3x3 Gaussian, depth max --------
+    for (int d = 0; d < D; ++d) {
+        if (!((mask >> d) & 1u)) {
+            if (P.dbg_grid) {
+                float *g = P.dbg_grid + ((size_t)b * D + d) * R * R;
+                for (int i = tid; i < R * R; i += NT) g[i] = 0.0f;
+            }
+            continue;
+        }
+        for (int i = tid; i < R * R / 4; i += NT)
+            reinterpret_cast<float4 *>(sm.G)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+        for (int i = tid; i < n; i += NT) {
+            float qx, qy, qz, val; int cell, zi;
+            rotate_point(pts + 3 * i, rm, fused, qx, qy, qz);
+            quantise(qx, qy, qz, nm, P, cell, zi, val);
+            // all values are positive floats: integer order == float order
+            if (zi == d) atomicMax(reinterpret_cast<int *>(sm.G) + cell, __float_as_int(val));
+        }
+        __syncthreads();
+        if (P.dbg_grid) {
+            float *g = P.dbg_grid + ((size_t)b * D + d) * R * R;
+            for (int i = tid; i < R * R; i += NT) g[i] = sm.G[i];
+            __syncthreads();
+        }
+
+        // horizontal 5-max in place, one warp per row: H(y,x) = max G(y, x-1..x+3), x in [0,110)
+        for (int r = 0; r < ROWS_PER_WARP; ++r) {
+            const int y = warp * ROWS_PER_WARP + r;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane < R / 4) a = reinterpret_cast<const float4 *>(sm.G + y * R)[lane];
+            const float left = __shfl_up_sync(0xffffffffu, a.w, 1);
+            const float rx = __shfl_down_sync(0xffffffffu, a.x, 1);
+            const float ry = __shfl_down_sync(0xffffffffu, a.y, 1);
+            const float rz = __shfl_down_sync(0xffffffffu, a.z, 1);
+            const float l = lane == 0 ? 0.0f : left;
+            const float m_yz = fmaxf(a.y, a.z), m_zw = fmaxf(a.z, a.w);
+            const float m_xyz = fmaxf(a.x, m_yz), m_yzw = fmaxf(a.y, m_zw);
+            float4 hmx;
+            hmx.x = fmaxf(fmaxf(l, a.w), m_xyz);
+            hmx.y = fmaxf(fmaxf(a.x, rx), m_yzw);
+            hmx.z = fmaxf(m_yzw, fmaxf(rx, ry));
+            hmx.w = fmaxf(m_zw, fmaxf(fmaxf(rx, ry), rz));
+            if (lane == R / 4 - 1) { hmx.z = 0.0f; hmx.w = 0.0f; }   // columns 110, 111: padding
+            __syncwarp();
+            if (lane < R / 4) reinterpret_cast<float4 *>(sm.G + y * R)[lane] = hmx;
+        }
+        __syncthreads();
+
+        // vertical 5-max in place: warp = 7-row chunk, lane = 4-column group.
+        // P(y,x) = max H(y-1..y+3, x); all loads precede all stores (barrier in between).
+        {
+            const int y0 = warp * ROWS_PER_WARP;
+            float4 h[ROWS_PER_WARP + 4];
+#pragma unroll
+            for (int k = 0; k < ROWS_PER_WARP + 4; ++k) {
+                const int y = y0 - 1 + k;
+                h[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (lane < R / 4 && y >= 0 && y < R)
+                    h[k] = reinterpret_cast<const float4 *>(sm.G + y * R)[lane];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < ROWS_PER_WARP; ++k) {
+                const int y = y0 + k;
+                float4 o = max4(max4(max4(h[k], h[k + 1]), max4(h[k + 2], h[k + 3])), h[k + 4]);
+                if (y >= Q) o = make_float4(0.f, 0.f, 0.f, 0.f);   // rows 110, 111: padding
+                if (lane < R / 4) reinterpret_cast<float4 *>(sm.G + y * R)[lane] = o;
+            }
+        }
+        __syncthreads();
+
+        // 3x3 Gaussian (zero padding) and running max over depth into IMG.
+        // acc = fma(w[i][j], P(y+i-1, x+j-1), acc) in row-major tap order.
+        {
+            const int y0 = warp * ROWS_PER_WARP;
+            float4 pa, pb, pc;          // rows y-1, y, y+1
+            float la, lb, lc, ra, rb, rc;
+            auto load_row = [&](int y, float4 &p, float &l, float &r) {
+                p = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (lane < R / 4 && y >= 0 && y < Q)
+                    p = reinterpret_cast<const float4 *>(sm.G + y * R)[lane];
+                l = __shfl_up_sync(0xffffffffu, p.w, 1);
+                r = __shfl_down_sync(0xffffffffu, p.x, 1);
+                if (lane == 0) l = 0.0f;
+            };
+            load_row(y0 - 1, pa, la, ra);
+            load_row(y0, pb, lb, rb);
+#pragma unroll
+            for (int k = 0; k < ROWS_PER_WARP; ++k) {
+                const int y = y0 + k;
+                load_row(y + 1, pc, lc, rc);
+                const float ta[6] = {la, pa.x, pa.y, pa.z, pa.w, ra};
+                const float tb[6] = {lb, pb.x, pb.y, pb.z, pb.w, rb};
+                const float tc[6] = {lc, pc.x, pc.y, pc.z, pc.w, rc};
+                float o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float acc = __fmul_rn(w[0], ta[j]);
+                    acc = __fmaf_rn(w[1], ta[j + 1], acc);
+                    acc = __fmaf_rn(w[2], ta[j + 2], acc);
+                    acc = __fmaf_rn(w[3], tb[j], acc);
+                    acc = __fmaf_rn(w[4], tb[j + 1], acc);
+                    acc = __fmaf_rn(w[5], tb[j + 2], acc);
+                    acc = __fmaf_rn(w[6], tc[j], acc);
+                    acc = __fmaf_rn(w[7], tc[j + 1], acc);
+                    acc = __fmaf_rn(w[8], tc[j + 2], acc);
+                    o[j] = acc;
+                }
+                if (lane == R / 4 - 1) { o[2] = 0.0f; o[3] = 0.0f; }
+                if (lane < R / 4 && y < Q) {
+                    float4 *dst = reinterpret_cast<float4 *>(sm.IMG + y * R) + lane;
+                    *dst = max4(*dst, make_float4(o[0], o[1], o[2], o[3]));
+                }
+                pa = pb; la = lb; ra = rb;
+                pb = pc; lb = lc; rb = rc;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- phase 4: img / max(img), 1 - x ---------------------------------------------------------
+    {
+        float m = 0.0f;
+        for (int i = tid; i < Q * R / 4; i += NT) {
+            const float4 t = reinterpret_cast<const float4 *>(sm.IMG)[i];
+            m = fmaxf(fmaxf(m, fmaxf(t.x, t.y)), fmaxf(t.z, t.w));
+        }
+        m = warp_max(m);
+        if (lane == 0) sm.red[warp] = m;
+        __syncthreads();
+        if (warp == 0) {
+            float t = lane < NW ? sm.red[lane] : 0.0f;
+            t = warp_max(t);
+            if (lane == 0) sm.mx = t;
+        }
+        __syncthreads();
+        const float mx = sm.mx;
+        for (int i = tid; i < Q * R / 4; i += NT) {
+            float4 t = reinterpret_cast<float4 *>(sm.IMG)[i];
+            t.x = __fsub_rn(1.0f, __fdiv_rn(t.x, mx));
+            t.y = __fsub_rn(1.0f, __fdiv_rn(t.y, mx));
+            t.z = __fsub_rn(1.0f, __fdiv_rn(t.z, mx));
+            t.w = __fsub_rn(1.0f, __fdiv_rn(t.w, mx));
+            reinterpret_cast<float4 *>(sm.IMG)[i] = t;
+        }
+        __syncthreads();
+        if (P.dbg_dens) {
+            float *dd = P.dbg_dens + (size_t)b * Q * Q;
+            for (int i = tid; i < Q * Q; i += NT) dd[i] = sm.IMG[(i / Q) * R + (i % Q)];
+        }
+    }
+
+    // ---- phase 5: bilinear 110 -> 224 (align_corners), floor(x*255), patch-major bf16 tiles ------
+    // Two halves: HI[y][ox] = fma(IMG[y][x0], lw0, IMG[y][x1]*lw1) for 56 source rows at a time
+    // (held in the grid buffer), then out = fma(HI[y0], lh0, HI[y1]*lh1) -- the exact contraction
+    // pattern of torch-CPU's separable interpolation on an FMA host.
+    __nv_bfloat16 *tile = P.tiles ? P.tiles + (size_t)b * VG_TILE_ELEMS : nullptr;
+    uint8_t *u8 = P.u8 ? P.u8 + (size_t)b * S * S : nullptr;
+    for (int half = 0; half < 2; ++half) {
+        const int ybase = half == 0 ? 0 : Q - HI_ROWS + 1;        // source rows 0..55 / 55..109
+        const int nrows = half == 0 ? HI_ROWS : Q - ybase;        // 56 / 55
+        const int oy_beg = half == 0 ? 0 : 113, oy_end = half == 0 ? 113 : S;
+        if (tid < 2 * S) {
+            const int ox = tid % S, rsel = tid / S;
+            int x0; float lw0, lw1;
+            lin_idx(ox, x0, lw0, lw1);
+            const int x1 = x0 + (x0 < Q - 1 ? 1 : 0);
+            for (int r = rsel; r < nrows; r += 2) {
+                const float *row = sm.IMG + (ybase + r) * R;
+                sm.G[r * S + ox] = __fmaf_rn(row[x0], lw0, __fmul_rn(row[x1], lw1));
+            }
+        }
+        __syncthreads();
+        const int items = (oy_end - oy_beg) * (S / 8);
+        for (int it = tid; it < items; it += NT) {
+            const int oy = oy_beg + it / (S / 8), g = it % (S / 8);
+            int y0; float lh0, lh1;
+            lin_idx(oy, y0, lh0, lh1);
+            const int y1 = y0 + (y0 < Q - 1 ? 1 : 0);
+            const float4 *r0 = reinterpret_cast<const float4 *>(sm.G + (y0 - ybase) * S + 8 * g);
+            const float4 *r1 = reinterpret_cast<const float4 *>(sm.G + (y1 - ybase) * S + 8 * g);
+            const float4 a0 = r0[0], a1 = r0[1], b0 = r1[0], b1 = r1[1];
+            const float ta[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float tb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            unsigned fb[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float o = __fmaf_rn(ta[j], lh0, __fmul_rn(tb[j], lh1));
+                const float s255 = __fmul_rn(o, 255.0f);
+                // np.uint8(x*255): truncation.  2^23 + s rounded toward zero leaves floor(s) in
+                // the low mantissa bits; subtracting 2^23 gives it back as an exact float.
+                const float t = __fadd_rz(s255, 8388608.0f);
+                fb[j] = __float_as_uint(__fsub_rn(t, 8388608.0f));
+            }
+            if (tile) {
+                // integers 0..255 are exact in bf16: the bf16 pattern is the high half of the fp32
+                uint4 pk;
+                pk.x = __byte_perm(fb[0], fb[1], 0x7632);
+                pk.y = __byte_perm(fb[2], fb[3], 0x7632);
+                pk.z = __byte_perm(fb[4], fb[5], 0x7632);
+                pk.w = __byte_perm(fb[6], fb[7], 0x7632);
+                const int patch = (oy >> 4) * 14 + (g >> 1);
+                const int inner = (oy & 15) * 16 + (g & 1) * 8;
+                *reinterpret_cast<uint4 *>(tile + patch * 256 + inner) = pk;
+            }
+            if (u8) {
+                unsigned lo = 0, hi = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    lo |= ((unsigned)__uint_as_float(fb[j])) << (8 * j);
+                    hi |= ((unsigned)__uint_as_float(fb[4 + j])) << (8 * j);
+                }
+                *reinterpret_cast<uint2 *>(u8 + oy * S + 8 * g) = make_uint2(lo, hi);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+int launch_projection(VgHandle *h, const float *d_points, const int32_t *d_offsets, int32_t C,
+                      __nv_bfloat16 *d_tiles, uint8_t *d_u8, int32_t *d_status,
+                      const VgProjectDebug *dbg, cudaStream_t st)
+{
+    const VgConfig &cfg = h->cfg;
+    if (cfg.resolution != R || cfg.depth != D || cfg.image_size != S) {
+        VG_SET_ERR(h, "projection kernel is specialised for R=112, D=8, S=224 (got %d, %d, %d)",
+                   cfg.resolution, cfg.depth, cfg.image_size);
+        return VG_ESHAPE;
+    }
+    if (C == 0) return VG_OK;
+    ProjParams P;
+    P.points = d_points;
+    P.offsets = d_offsets;
+    P.C = C;
+    P.V = cfg.num_views;
+    memcpy(P.rot, cfg.rot, sizeof(P.rot));
+    memcpy(P.gauss, cfg.gauss, sizeof(P.gauss));
+    P.obj_ratio = (float)cfg.obj_ratio;
+    P.depth_bias = (float)cfg.depth_bias;
+    P.one_plus_bias = (float)(1.0 + cfg.depth_bias);
+    P.rotate_mode = cfg.rotate_mode;
+    P.tiles = d_tiles;
+    P.u8 = d_u8;
+    P.status = d_status;
+    P.dbg_grid = dbg ? dbg->d_grid : nullptr;
+    P.dbg_dens = dbg ? dbg->d_densified : nullptr;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VG_CUDA_CHECK(h, cudaFuncSetAttribute(projection_kernel,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)sizeof(Smem)));
+        attr_set = true;
+    }
+    const long long blocks = (long long)C * cfg.num_views;
+    projection_kernel<<<(unsigned)blocks, NT, sizeof(Smem), st>>>(P);
+    VG_LAUNCH_CHECK(h);
+    return VG_OK;
+}
+
+}  // namespace vg
