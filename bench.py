@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""Benchmark of the ViLGOD classification hot path on B200 (contract: see the task description).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): a Waymo-shaped batch of 64 frames x ~300 clusters
+(10..2048 points, log-uniform), 10-view 224x224 projection, CLIP ViT-B/16 (random-init weights,
+bf16 GEMM operands) zero-shot scoring against 24 prompts, per-cluster view vote.  One "step" is one
+pass of the whole hot path over the whole batch.  Under torchrun every rank owns its own 64-frame
+batch (frames shard with no data-path collective, weak scaling) and the job-wide value is the sum.
+
+Printed JSON line: metric clusters/s with `value` (inputs resident in HBM), `e2e` (host buffers,
+H2D + D2H inside the timed region), `roofline` (GEMM kernels vs the measured bf16 peak, from CUDA
+events around every launch), `roofline_projection` (vs measured HBM peak), `cpu_baseline` (the
+oracle port of the reference path on the host cores, bounded sample), clocks and launch counts.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "clusters_per_second"
+UNIT = "clusters/s"
+FLOP_PER_IMAGE = 35.127e9     # 17,563,453,440 MAC per ViT-B/16 image
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=64)
+    ap.add_argument("--clusters-per-frame", type=int, default=300)
+    ap.add_argument("--views", type=int, default=10)
+    ap.add_argument("--n-max", type=int, default=2048)
+    ap.add_argument("--cpu-sample-clusters", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed", type=int, default=20240807)
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"waymo-shaped batch: {a.frames} frames x ~{a.clusters_per_frame} clusters "
+            f"(10..{a.n_max} pts), {a.views}-view 224x224 projection + ViT-B/16 zero-shot scoring "
+            f"(24 prompts) + view vote")
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json: hbm_gbs, bf16_tflops_sustained)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        # samples under load = upper half (the sampler also sees idle gaps between steps)
+        sm_sorted = sorted(sm)
+        return dict(sm_mhz=statistics.median(sm_sorted[len(sm_sorted) // 2:]) if sm else None,
+                    sm_max_mhz=max(mx) if mx else None, power_w_max=max(power) if power else None,
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step(points, offsets, views, weights, text, threads):
+    from oracle import pipeline as opipe
+    return opipe.classify(points, offsets, views, weights, text, threads=threads)
+
+
+def make_cpu_sample(a, seed):
+    from vilgod_b200 import synthetic
+    rng = np.random.default_rng(seed)
+    return synthetic.make_clusters(a.cpu_sample_clusters, n_min=10, n_max=a.n_max, rng=rng)
+
+
+def run_reference_arm(a):
+    """--impl reference: the reference's CPU implementation of the path, as the oracle port
+    (the reference is Python and cannot travel to the GPU box; oracle/ is pinned against it by the
+    golden vectors), all host threads, bounded sample per step."""
+    import torch
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    from oracle import vit as ovit
+    from vilgod_b200 import weights as vw
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    w = ovit.make_visual_weights(1234)
+    text = vw.synthetic_text_features(24).numpy()
+    pts, off = make_cpu_sample(a, a.seed)
+    C = len(off) - 1
+    for _ in range(max(a.warmup, 0)):
+        cpu_reference_step(pts, off, a.views, w, text, cores)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        cpu_reference_step(pts, off, a.views, w, text, cores)
+    dt = time.perf_counter() - t0
+    val = C * a.steps / dt
+    sample = (f"{C} clusters x {a.views} views per step ({C * a.views} images) drawn from the same "
+              f"generator as the workload; fp32 torch-CPU ViT + C projection oracle")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": workload_name(a), "views": a.views,
+                                            "sample_clusters_per_step": C},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from vilgod_b200 import sharding, synthetic, weights as vw
+    from vilgod_b200.engine import Engine
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a B200; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    # --- workload: every rank owns `frames` frames of the global (frames * world)-frame batch ---
+    gframes = sharding.frames_of_rank(a.frames * world, rank, world)
+    frames = []
+    for f in gframes:
+        rng = np.random.default_rng([a.seed, f])
+        c = max(1, int(rng.poisson(a.clusters_per_frame)))
+        frames.append(synthetic.make_clusters(c, n_min=10, n_max=a.n_max, rng=rng))
+    pts_np, off_np, bounds = synthetic.concat_frames(frames)
+    C = len(off_np) - 1
+    V = a.views
+    total_points = int(off_np[-1])
+
+    eng = Engine(num_views=V)
+    eng.load_vit_weights(vw.random_init_visual_state_dict(1234))
+    text = vw.synthetic_text_features(24)
+    eng.set_text_features(text)
+
+    d_pts = torch.from_numpy(pts_np).cuda()
+    d_off = torch.from_numpy(off_np).cuda()
+    out = eng.alloc_outputs(C, want_feats=True)
+    eng.workspace(C * V)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        eng.classify(d_pts, d_off, out=out)
+
+    # pinned host staging for the end-to-end arm
+    h_pts = torch.from_numpy(pts_np).pin_memory()
+    h_off = torch.from_numpy(off_np).pin_memory()
+    e_pts = torch.empty_like(d_pts)
+    e_off = torch.empty_like(d_off)
+    h_res = {k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory()
+             for k in ("voted_class", "voted_score", "top1", "status")}
+    frame_of_cluster = torch.from_numpy(
+        np.repeat(np.asarray(gframes), np.diff(bounds)).astype(np.int64)).cuda()
+    cluster_index = torch.from_numpy(
+        np.concatenate([np.arange(n) for n in np.diff(bounds)]).astype(np.int64)).cuda()
+
+    def step_e2e():
+        e_pts.copy_(h_pts, non_blocking=True)
+        e_off.copy_(h_off, non_blocking=True)
+        eng.classify(e_pts, e_off, out=out)
+        for k, t in h_res.items():
+            t.copy_(out[k], non_blocking=True)
+        if world > 1:   # the only exchange on the path: final per-cluster labels to rank 0
+            sharding.gather_labels(frame_of_cluster, cluster_index, out["voted_class"],
+                                   out["voted_score"])
+        torch.cuda.current_stream().synchronize()
+
+    h2d = pts_np.nbytes + off_np.nbytes
+    d2h = sum(t.numel() * t.element_size() for t in h_res.values())
+
+    for _ in range(max(a.warmup, 3)):
+        step_resident()
+    barrier()
+
+    # --- timed region 1: device-resident, K steps, CUDA events, L2 flushed between steps ---
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(a.steps)]
+    barrier()
+    for s, e in ev:
+        s.record()
+        step_resident()
+        e.record()
+        flush.zero_()            # untimed: evict L2 between steps
+    barrier()
+    launches = eng.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = sum(s.elapsed_time(e) for s, e in ev)
+
+    # --- timed region 2: same K steps with an event pair around every kernel launch ---
+    eng.profile_begin()
+    barrier()
+    for _ in range(a.steps):
+        step_resident()
+        flush.zero_()
+    barrier()
+    prof = eng.profile_end()
+
+    # --- timed region 3: end to end through the host-buffer call ---
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    # host-visible time: the call returns only after the results are in pinned host memory
+    e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))
+
+    # max over ranks of the times, sum over ranks of the units
+    stats = torch.tensor([ms_total, e2e_ms, float(C)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms_total, e2e_ms, C_all = float(mx[0]), float(mx[1]), float(sm[2])
+    else:
+        C_all = float(C)
+
+    if rank == 0:
+        peaks = load_peaks()
+        value = C_all * a.steps / (ms_total * 1e-3)
+        e2e_val = C_all * a.steps / (e2e_ms * 1e-3)
+        gemm_keys = ["gemm_patch", "gemm_qkv", "gemm_out", "gemm_fc", "gemm_proj"]
+        g_ms = sum(prof[k]["ms"] for k in gemm_keys)
+        g_fl = sum(prof[k]["work"] for k in gemm_keys)
+        g_n = sum(prof[k]["launches"] for k in gemm_keys)
+        all_ms = sum(v["ms"] for v in prof.values())
+        gemm_tflops = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        roofline = {"bound": "tensor", "kernel": "gemm_kernel<*> (tcgen05, all five ViT GEMM shapes)",
+                    "achieved": gemm_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": gemm_tflops / peaks["bf16_tflops"], "traffic": traffic,
+                    "peak_source": peaks["source"], "launches": g_n,
+                    "avg_launch_ms": g_ms / max(g_n, 1), "share_of_step": g_ms / max(all_ms, 1e-9)}
+        p = prof["projection"]
+        proj_bytes = p["work"] + 12.0 * total_points * a.steps
+        proj_gbs = proj_bytes / (p["ms"] * 1e-3) / 1e9 if p["ms"] > 0 else 0.0
+        roofline_proj = {"bound": "hbm", "kernel": "projection_kernel", "achieved": proj_gbs,
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": proj_gbs / peaks["hbm_gbs"],
+                         "traffic": None, "launches": p["launches"],
+                         "avg_launch_ms": p["ms"] / max(p["launches"], 1),
+                         "share_of_step": p["ms"] / max(all_ms, 1e-9)}
+        vit_ms = all_ms - p["ms"] - prof["vote"]["ms"]
+        images = C * V * a.steps
+        vit_frac = FLOP_PER_IMAGE * images / (vit_ms * 1e-3) / 1e12 / peaks["bf16_tflops"] if vit_ms > 0 else 0
+        breakdown = {k: {"ms_per_step": v["ms"] / a.steps, "launches_per_step": v["launches"] // a.steps}
+                     for k, v in prof.items()}
+        cpu_baseline = None
+        if world == 1 and not a.no_cpu_baseline:
+            from oracle import vit as ovit
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            spts, soff = make_cpu_sample(a, a.seed)
+            w = ovit.make_visual_weights(1234)
+            t0 = time.perf_counter()
+            cpu_reference_step(spts, soff, V, w, text.numpy(), cores)
+            dt = time.perf_counter() - t0
+            cpu_baseline = {"value": (len(soff) - 1) / dt, "unit": UNIT, "cores": cores,
+                            "kind": "port",
+                            "sample": f"{len(soff) - 1} clusters x {V} views "
+                                      f"({(len(soff) - 1) * V} images), one pass, {dt:.1f} s"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": ms_total / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(a), "clusters_per_rank": C, "views": V,
+                       "images_per_step_per_rank": C * V, "points_per_rank": total_points,
+                       "weights": "random-init ViT-B/16 (seed 1234, fp16-rounded like build_model)",
+                       "l2": "256 MiB buffer written between timed steps (L2 flush); per-step "
+                             "working set (~GBs of activations) >> 126 MB L2",
+                       "parallelism": f"frames sharded over {world} rank(s), no data-path collective"},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / a.steps},
+            "gpu_launches": launches,
+            "roofline": roofline, "roofline_projection": roofline_proj,
+            "vit_tensor_frac_of_peak": vit_frac,
+            "images_per_second": C_all * V * a.steps / (ms_total * 1e-3),
+            "kernel_breakdown_rank0": breakdown, "clocks": clocks, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -173,6 +173,21 @@ VG_API int vg_test_attention(VgHandle *h, const void *d_qkv, int64_t B, void *d_
 /* x [rows,768] fp32 -> y bf16 [rows,768] = LayerNorm(x) * w + b */
 VG_API int vg_test_layernorm(VgHandle *h, const float *d_x, const float *d_w, const float *d_b,
                       int64_t rows, void *d_y, void *stream);
+/* ---- live per-kernel timing (CUDA events on the caller's stream, around every launch) ---- */
+enum { VG_K_PROJECTION = 0, VG_K_GEMM_PATCH, VG_K_GEMM_QKV, VG_K_GEMM_OUT, VG_K_GEMM_FC,
+       VG_K_GEMM_PROJ, VG_K_ATTENTION, VG_K_LAYERNORM, VG_K_LN_PRE, VG_K_HEAD, VG_K_VOTE,
+       VG_K_COUNT };
+typedef struct VgKernelTimes {
+    double ms[VG_K_COUNT];       /* summed device time per kernel class */
+    int64_t launches[VG_K_COUNT];
+    double work[VG_K_COUNT];     /* summed algorithmic work: FLOPs for GEMM / attention classes,
+                                    bytes for the memory-bound classes */
+} VgKernelTimes;
+/* start recording an event pair around every kernel launch on this handle */
+VG_API int vg_profile_begin(VgHandle *h);
+/* stop recording, synchronise the recorded events and return the per-class totals */
+VG_API int vg_profile_end(VgHandle *h, VgKernelTimes *out);
+
 /* number of kernel launches the library has issued on this handle (for bench.py's gpu_launches) */
 VG_API int64_t vg_launch_count(const VgHandle *h);
 

@@ -50,6 +50,15 @@ class VgProjectDebug(C.Structure):
     _fields_ = [("d_grid", C.c_void_p), ("d_densified", C.c_void_p)]
 
 
+VG_K_NAMES = ["projection", "gemm_patch", "gemm_qkv", "gemm_out", "gemm_fc", "gemm_proj",
+              "attention", "layernorm", "ln_pre", "head", "vote"]
+
+
+class VgKernelTimes(C.Structure):
+    _fields_ = [("ms", C.c_double * len(VG_K_NAMES)), ("launches", C.c_int64 * len(VG_K_NAMES)),
+                ("work", C.c_double * len(VG_K_NAMES))]
+
+
 class VgVitDebug(C.Structure):
     _fields_ = [("stop_after_layer", C.c_int32), ("d_x", C.c_void_p)]
 
@@ -61,6 +70,8 @@ SYMBOLS = {
     "vg_destroy": (None, [C.c_void_p]),
     "vg_last_error": (C.c_char_p, [C.c_void_p]),
     "vg_launch_count": (C.c_int64, [C.c_void_p]),
+    "vg_profile_begin": (C.c_int, [C.c_void_p]),
+    "vg_profile_end": (C.c_int, [C.c_void_p, C.POINTER(VgKernelTimes)]),
     "vg_load_vit_weights": (C.c_int, [C.c_void_p, C.POINTER(VgVitWeights), C.c_void_p]),
     "vg_set_text_features": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32),
                                        C.c_int32, C.c_void_p]),

@@ -122,12 +122,42 @@ void vg_destroy(VgHandle *h)
     if (h->arena) cudaFree(h->arena);
     if (h->d_text) cudaFree(h->d_text);
     if (h->d_class_map) cudaFree(h->d_class_map);
+    for (auto &r : h->prof) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }
+    for (auto e : h->event_pool) cudaEventDestroy(e);
     delete h;
 }
 
 const char *vg_last_error(const VgHandle *h) { return h ? h->err : "null handle"; }
 
 int64_t vg_launch_count(const VgHandle *h) { return h ? h->launches : 0; }
+
+int vg_profile_begin(VgHandle *h)
+{
+    if (!h) return VG_EINVAL;
+    for (auto &r : h->prof) { h->event_pool.push_back(r.start); h->event_pool.push_back(r.stop); }
+    h->prof.clear();
+    h->profiling = true;
+    return VG_OK;
+}
+
+int vg_profile_end(VgHandle *h, VgKernelTimes *out)
+{
+    if (!h || !out) return VG_EINVAL;
+    h->profiling = false;
+    memset(out, 0, sizeof(*out));
+    for (auto &r : h->prof) {
+        VG_CUDA_CHECK(h, cudaEventSynchronize(r.stop));
+        float ms = 0.0f;
+        VG_CUDA_CHECK(h, cudaEventElapsedTime(&ms, r.start, r.stop));
+        out->ms[r.kind] += ms;
+        out->launches[r.kind] += 1;
+        out->work[r.kind] += r.work;
+        h->event_pool.push_back(r.start);
+        h->event_pool.push_back(r.stop);
+    }
+    h->prof.clear();
+    return VG_OK;
+}
 
 int vg_load_vit_weights(VgHandle *h, const VgVitWeights *w, void *stream)
 {

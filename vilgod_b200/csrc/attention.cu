@@ -211,6 +211,7 @@ int launch_attention(VgHandle *h, const __nv_bfloat16 *qkv, int64_t B, __nv_bflo
                                               (int)ATT_SMEM));
         attr_set = true;
     }
+    VgProfScope prof(h, VG_K_ATTENTION, 4.0 * (double)B * kHeads * L * L * HD, st);
     attention_kernel<<<(unsigned)(B * kHeads), ATT_THREADS, ATT_SMEM, st>>>(qkv, out);
     VG_LAUNCH_CHECK(h);
     return VG_OK;

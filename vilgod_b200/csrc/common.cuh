@@ -8,6 +8,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <vector>
+
 #include "../../include/vilgod_b200.h"
 
 namespace vg {
@@ -40,8 +42,17 @@ struct VitDev {
 
 }  // namespace vg
 
+struct VgProfRecord {
+    cudaEvent_t start, stop;
+    int kind;
+    double work;
+};
+
 struct VgHandle {
     VgConfig cfg;
+    bool profiling = false;
+    std::vector<VgProfRecord> prof;
+    std::vector<cudaEvent_t> event_pool;
     int device = 0;
     int num_sms = 148;
     char err[512];
@@ -75,6 +86,33 @@ struct VgHandle {
         (h)->launches++;                                     \
         VG_CUDA_CHECK(h, cudaGetLastError());                \
     } while (0)
+
+// RAII event pair around one kernel launch (active only between vg_profile_begin/_end)
+struct VgProfScope {
+    VgHandle *h;
+    cudaStream_t st;
+    cudaEvent_t stop = nullptr;
+    VgProfScope(VgHandle *h_, int kind, double work, cudaStream_t st_) : h(h_), st(st_)
+    {
+        if (!h->profiling) return;
+        cudaEvent_t ev[2];
+        for (int i = 0; i < 2; ++i) {
+            if (!h->event_pool.empty()) {
+                ev[i] = h->event_pool.back();
+                h->event_pool.pop_back();
+            } else {
+                cudaEventCreate(&ev[i]);
+            }
+        }
+        cudaEventRecord(ev[0], st);
+        stop = ev[1];
+        h->prof.push_back(VgProfRecord{ev[0], ev[1], kind, work});
+    }
+    ~VgProfScope()
+    {
+        if (stop) cudaEventRecord(stop, st);
+    }
+};
 
 // kernel launchers implemented in the .cu files ------------------------------------------------
 namespace vg {

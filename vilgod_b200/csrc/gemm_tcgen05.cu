@@ -273,6 +273,13 @@ int launch_gemm_t(VgHandle *h, const GemmArgs &g, cudaStream_t st)
     p.K = g.K;
     const int64_t tiles = ((g.M + BM - 1) / BM) * (g.N / BN);
     const int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+    const int kind = EPI == kEpiPatch ? VG_K_GEMM_PATCH
+                     : EPI == VG_EPI_BIAS_BF16 ? VG_K_GEMM_QKV
+                     : EPI == VG_EPI_BIAS_QGELU_BF16 ? VG_K_GEMM_FC
+                     : (g.K == kMlp ? VG_K_GEMM_PROJ : VG_K_GEMM_OUT);
+    // algorithmic FLOPs; the patch embedding is credited with the un-folded K = 3*16*16
+    const double kk = EPI == kEpiPatch ? 768.0 : (double)g.K;
+    VgProfScope prof(h, kind, 2.0 * (double)g.M * g.N * kk, st);
     gemm_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ta, tb, p);
     VG_LAUNCH_CHECK(h);
     return VG_OK;

@@ -476,6 +476,8 @@ int launch_projection(VgHandle *h, const float *d_points, const int32_t *d_offse
         attr_set = true;
     }
     const long long blocks = (long long)C * cfg.num_views;
+    // algorithmic bytes recorded here: the emitted tiles; the caller adds 12 * sum(N) for the points
+    VgProfScope prof(h, VG_K_PROJECTION, (double)blocks * VG_TILE_ELEMS * 2.0, st);
     projection_kernel<<<(unsigned)blocks, NT, sizeof(Smem), st>>>(P);
     VG_LAUNCH_CHECK(h);
     return VG_OK;

@@ -289,6 +289,7 @@ int launch_layernorm_bf16(VgHandle *h, const float *x, const float *w, const flo
                           __nv_bfloat16 *y, cudaStream_t st)
 {
     if (rows <= 0) return VG_OK;
+    VgProfScope prof(h, VG_K_LAYERNORM, (double)rows * kWidth * 6.0, st);
     layernorm_bf16_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, w, b, rows, y);
     VG_LAUNCH_CHECK(h);
     return VG_OK;
@@ -298,6 +299,7 @@ int launch_ln_pre(VgHandle *h, float *x, int64_t B, cudaStream_t st)
 {
     const int64_t rows = B * kTokens;
     if (rows <= 0) return VG_OK;
+    VgProfScope prof(h, VG_K_LN_PRE, (double)rows * kWidth * 8.0, st);
     ln_pre_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, h->vit.patch_bias_pos,
                                                               h->vit.ln_pre_w, h->vit.ln_pre_b, rows);
     VG_LAUNCH_CHECK(h);
@@ -308,6 +310,7 @@ int launch_head(VgHandle *h, const float *x, int64_t B, float *probs, int32_t *t
                 float *logits, cudaStream_t st)
 {
     if (B <= 0) return VG_OK;
+    VgProfScope prof(h, VG_K_HEAD, (double)B * kWidth * 4.0, st);
     head_kernel<<<(unsigned)B, 256, 0, st>>>(x, h->vit.ln_post_w, h->vit.ln_post_b, h->vit.proj,
                                              h->d_text, h->num_prompts, (float)h->cfg.logit_scale,
                                              probs, top1, feats, logits);
@@ -319,6 +322,7 @@ int launch_vote(VgHandle *h, const float *probs, const int32_t *top1, int32_t C,
                 int32_t *voted_class, float *voted_score, cudaStream_t st)
 {
     if (C <= 0) return VG_OK;
+    VgProfScope prof(h, VG_K_VOTE, (double)C * h->cfg.num_views * 8.0, st);
     vote_kernel<<<(C + 127) / 128, 128, 0, st>>>(probs, top1, h->d_class_map, C, h->cfg.num_views,
                                                  h->num_prompts, h->num_classes, voted_class,
                                                  voted_score);

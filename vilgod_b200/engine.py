@@ -260,6 +260,16 @@ class Engine:
             voted_score=torch.empty((Cn,), dtype=torch.float32, device=d),
             status=torch.empty((Cn,), dtype=torch.int32, device=d))
 
+    def profile_begin(self):
+        self._check(self.lib.vg_profile_begin(self._h))
+
+    def profile_end(self):
+        """-> {kernel class: dict(ms, launches, work)} from CUDA events around every launch."""
+        kt = _lib.VgKernelTimes()
+        self._check(self.lib.vg_profile_end(self._h, C.byref(kt)))
+        return {n: dict(ms=kt.ms[i], launches=int(kt.launches[i]), work=kt.work[i])
+                for i, n in enumerate(_lib.VG_K_NAMES)}
+
     # kernel-level hooks used by the tests -----------------------------------------------------
     def test_gemm(self, a, w, bias, epilogue, out=None):
         M, K = a.shape
