@@ -11,7 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(OUT_DIR, "libvilgod_b200.so")
-SOURCES = ["api.cu", "projection.cu", "gemm_tcgen05.cu", "attention.cu", "vit_misc.cu"]
+SOURCES = ["api.cu", "projection.cu", "gemm_tcgen05.cu", "gemm_tcgen05_2cta.cu", "attention.cu",
+           "vit_misc.cu"]
 HEADERS = ["common.cuh", "ptx.cuh", os.path.join("..", "..", "include", "vilgod_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

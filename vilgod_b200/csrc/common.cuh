@@ -133,6 +133,7 @@ struct GemmArgs {
 };
 constexpr int kEpiPatch = 3;  // out fp32 x[img*197 + 1 + p][n] = acc + table[1+p][n]
 int launch_gemm(VgHandle *h, const GemmArgs &g, cudaStream_t st);
+int launch_gemm_2cta(VgHandle *h, const GemmArgs &g, cudaStream_t st);   // cta_group::2 path
 
 int launch_attention(VgHandle *h, const __nv_bfloat16 *qkv, int64_t B, __nv_bfloat16 *out,
                      cudaStream_t st);

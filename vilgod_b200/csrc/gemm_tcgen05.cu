@@ -17,6 +17,7 @@
 // Synchronisation is mbarrier-only: full/empty per smem stage (TMA tx-count / tcgen05.commit) and
 // full/empty per accumulator stage (tcgen05.commit / 128 epilogue arrivals).
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -300,6 +301,10 @@ int launch_gemm(VgHandle *h, const GemmArgs &g, cudaStream_t st)
         VG_SET_ERR(h, "gemm: operands must be 16-byte aligned");
         return VG_EINVAL;
     }
+    // production path: 2-CTA kernel with TMA-store epilogues (gemm_tcgen05_2cta.cu).  The single-CTA
+    // kernel below serves the patch embedding (row-remapping epilogue) and VG_GEMM_V1=1 (A/B runs).
+    static const bool force_v1 = getenv("VG_GEMM_V1") != nullptr;
+    if (g.epilogue != kEpiPatch && !force_v1) return launch_gemm_2cta(h, g, st);
     switch (g.epilogue) {
         case VG_EPI_BIAS_BF16: return launch_gemm_t<VG_EPI_BIAS_BF16>(h, g, st);
         case VG_EPI_BIAS_QGELU_BF16: return launch_gemm_t<VG_EPI_BIAS_QGELU_BF16>(h, g, st);

@@ -1,0 +1,355 @@
+// 2-CTA (cta_group::2) persistent bf16 GEMM with TMA-store epilogues -- the production path for
+// the QKV / out-proj / MLP layers of the CLIP visual tower (third_party/CLIP/clip/model.py:177-192).
+//
+//   D[M,N] = epilogue( A[M,K] . W[N,K]^T + bias[N] )
+//
+// Why a CTA pair: a single-CTA 128x256 SS-mode MMA streams 12 KB of operands per K=16 step out of
+// shared memory while TMA writes the same amount in -- 192 B/clk against a 128 B/clk shared-memory
+// port, which capped the first kernel at ~67 % tensor-pipe activity (profiles/r01_ncu_v1_*).  With
+// cta_group::2 the pair computes a 256x256 tile, each CTA stages its own 128 A rows and only HALF
+// of the W tile (128 rows); the tensor cores read the other half from the peer's shared memory.
+//
+// Per CTA (6 warps), clusters of 2 CTAs, one cluster per SM pair, static round-robin over tiles:
+//   warp 0     TMA producer (both CTAs): A 128x64 + W 128x64 per stage, bytes credited to the
+//              LEADER's full barrier (cp.async.bulk.tensor ... cta_group::2)
+//   warp 1     leader only: tcgen05.mma.cta_group::2 (UMMA 256x256x16), multicast tcgen05.commit
+//              frees the stage in both CTAs / publishes the accumulator to both epilogues
+//   warps 2-5  epilogue (both CTAs, 32 TMEM lanes each): tcgen05.ld -> registers -> bias /
+//              QuickGELU / residual -> swizzled staging slab in shared memory -> TMA store
+//              (coalesced, asynchronous, clips the ragged last M tile).  The fp32 residual stream is
+//              TMA-loaded into the slab one chunk ahead, so the epilogue issues no per-thread global
+//              loads or stores at all.
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace vg {
+namespace {
+
+constexpr int BM = 128;            // rows per CTA (256 per pair)
+constexpr int BN = 256;            // UMMA N; each CTA stages BN/2 rows of W
+constexpr int BK = 64, UK = 16;
+constexpr int STAGES = 4;
+constexpr int ACC_STAGES = 2;
+constexpr int A_BYTES = BM * BK * 2;          // 16 KiB
+constexpr int B_BYTES = (BN / 2) * BK * 2;    // 16 KiB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int THREADS = 192;
+constexpr int EPI_WARPS = 4;
+constexpr int SLAB_BYTES = 4096;              // 32 rows x 128 B, SWIZZLE_128B
+constexpr int SLABS_PER_WARP = 4;             // bf16: 2 out; f32: 2 in + 2 out
+constexpr int EPI_BYTES = EPI_WARPS * SLABS_PER_WARP * SLAB_BYTES;   // 64 KiB
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 512;
+
+struct Params {
+    const float *bias;
+    int64_t M;
+    int32_t N, K;
+};
+
+__device__ __forceinline__ float quick_gelu(float v)
+{
+    return __fdividef(v, 1.0f + __expf(-1.702f * v));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b)
+{
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&t);
+}
+// 16-byte chunk c of row r inside a 1024-byte-aligned SWIZZLE_128B slab
+__device__ __forceinline__ uint32_t slab_off(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+             const __grid_constant__ CUtensorMap tma_out, const Params p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    unsigned char *epi_smem = smem + (size_t)STAGES * STAGE_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(epi_smem + EPI_BYTES);
+    uint64_t *full_bar = bars;                               // [STAGES]   (leader's are used)
+    uint64_t *empty_bar = bars + STAGES;                     // [STAGES]   (per CTA)
+    uint64_t *tmem_full = bars + 2 * STAGES;                 // [ACC]      (per CTA)
+    uint64_t *tmem_empty = bars + 2 * STAGES + ACC_STAGES;   // [ACC]      (leader's are used)
+    uint64_t *xin_bar = bars + 2 * STAGES + 2 * ACC_STAGES;  // [EPI_WARPS][2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(xin_bar + 2 * EPI_WARPS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const int m_tiles = (int)((p.M + 2 * BM - 1) / (2 * BM));
+    const int n_tiles = p.N / BN;
+    const int num_tiles = m_tiles * n_tiles;
+    const int num_kb = p.K / BK;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tma_a);
+        ptx::prefetch_tensormap(&tma_b);
+        ptx::prefetch_tensormap(&tma_out);
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < ACC_STAGES; ++s) {
+            ptx::mbar_init(&tmem_full[s], 1);
+            ptx::mbar_init(&tmem_empty[s], 2 * EPI_WARPS);   // one arrival per epilogue warp, both CTAs
+        }
+        for (int s = 0; s < 2 * EPI_WARPS; ++s) ptx::mbar_init(&xin_bar[s], 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc_pair(tmem_slot, ACC_STAGES * BN);
+        ptx::tmem_relinquish_pair();
+    }
+    ptx::tc_fence_before();
+    __syncwarp();
+    ptx::cluster_sync_all();     // peer barriers initialised, both TMEM allocations done
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs) =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+                const int a_row = m_blk * 2 * BM + (int)rank * BM;
+                const int b_row = n_blk * BN + (int)rank * (BN / 2);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    unsigned char *sa = smem + (size_t)stage * STAGE_BYTES;
+                    if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+                    ptx::tma_load_2d_pair(sa, &tma_a, &full_bar[stage], kb * BK, a_row);
+                    ptx::tma_load_2d_pair(sa + A_BYTES, &tma_b, &full_bar[stage], kb * BK, b_row);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA, one lane) =================
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(2 * BM, BN);
+            int stage = 0, as = 0;
+            uint32_t phase = 0, aphase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                ptx::mbar_wait(&tmem_empty[as], aphase ^ 1u);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * STAGE_BYTES);
+                    const uint64_t da = ptx::make_kmajor_sw128_desc(sa);
+                    const uint64_t db = ptx::make_kmajor_sw128_desc(sa + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UK; ++k)
+                        ptx::mma_f16_ss_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k),
+                                             idesc, (uint32_t)((kb | k) != 0));
+                    ptx::tc_commit_pair(&empty_bar[stage], 3);   // stage free in both CTAs
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                ptx::tc_commit_pair(&tmem_full[as], 3);          // accumulator ready in both CTAs
+                if (++as == ACC_STAGES) { as = 0; aphase ^= 1u; }
+            }
+        }
+    } else {
+        // ================= epilogue warps (both CTAs) =================
+        const int ew = warp & 3;                  // TMEM lane quarter this warp may touch
+        const int lane_base = ew * 32;
+        unsigned char *slab = epi_smem + (size_t)ew * SLABS_PER_WARP * SLAB_BYTES;
+        uint64_t *xbar = xin_bar + 2 * ew;
+        uint32_t xphase[2] = {0u, 0u};
+        int as = 0;
+        uint32_t aphase = 0;
+        int obuf = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+            const int row0 = m_blk * 2 * BM + (int)rank * BM + lane_base;   // first row of the slab
+            const int col0 = n_blk * BN;
+            const uint32_t tbase = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(as * BN);
+
+            if (EPI == VG_EPI_BIAS_RESID_F32) {
+                // fp32 residual stream: 8 chunks of 32 columns; x chunk j+1 is in flight while
+                // chunk j is combined.  slabs 0,1 = x in, slabs 2,3 = x out.
+                if (lane == 0) {
+                    ptx::mbar_arrive_expect_tx(&xbar[0], SLAB_BYTES);
+                    ptx::tma_load_2d(slab, &tma_out, &xbar[0], col0, row0);
+                }
+                ptx::mbar_wait(&tmem_full[as], aphase);
+                ptx::tc_fence_after();
+#pragma unroll 1
+                for (int ch = 0; ch < BN / 32; ++ch) {
+                    const int ib = ch & 1;
+                    if (lane == 0 && ch + 1 < BN / 32) {
+                        // slab (ib^1) was fully read in iteration ch-1 (warp-synchronous below)
+                        ptx::mbar_arrive_expect_tx(&xbar[ib ^ 1], SLAB_BYTES);
+                        ptx::tma_load_2d(slab + (ib ^ 1) * SLAB_BYTES, &tma_out, &xbar[ib ^ 1],
+                                         col0 + (ch + 1) * 32, row0);
+                    }
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32b_x32(tbase + (uint32_t)(ch * 32), r);
+                    // the out slab about to be overwritten must have been drained by its TMA store
+                    if (lane == 0) ptx::tma_store_wait_read<1>();
+                    __syncwarp();
+                    ptx::mbar_wait(&xbar[ib], xphase[ib]);
+                    xphase[ib] ^= 1u;
+                    ptx::tmem_ld_wait();
+                    const unsigned char *xin = slab + ib * SLAB_BYTES;
+                    unsigned char *xout = slab + (2 + obuf) * SLAB_BYTES;
+                    const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + col0 + ch * 32);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint32_t off = slab_off(lane, q);
+                        const float4 x = *reinterpret_cast<const float4 *>(xin + off);
+                        const float4 bv = __ldg(b4 + q);
+                        float4 o;
+                        o.x = x.x + (__uint_as_float(r[4 * q + 0]) + bv.x);
+                        o.y = x.y + (__uint_as_float(r[4 * q + 1]) + bv.y);
+                        o.z = x.z + (__uint_as_float(r[4 * q + 2]) + bv.z);
+                        o.w = x.w + (__uint_as_float(r[4 * q + 3]) + bv.w);
+                        *reinterpret_cast<float4 *>(xout + off) = o;
+                    }
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::tma_store_2d(&tma_out, xout, col0 + ch * 32, row0);
+                        ptx::tma_store_commit();
+                    }
+                    obuf ^= 1;
+                }
+            } else {
+                // bf16 output: 4 chunks of 64 columns, slabs 0,1 = out (2 x [32 rows x 64 bf16])
+                ptx::mbar_wait(&tmem_full[as], aphase);
+                ptx::tc_fence_after();
+#pragma unroll 1
+                for (int ch = 0; ch < BN / 64; ++ch) {
+                    uint32_t r0[32], r1[32];
+                    ptx::tmem_ld_32x32b_x32(tbase + (uint32_t)(ch * 64), r0);
+                    ptx::tmem_ld_32x32b_x32(tbase + (uint32_t)(ch * 64 + 32), r1);
+                    if (lane == 0) ptx::tma_store_wait_read<1>();
+                    __syncwarp();
+                    ptx::tmem_ld_wait();
+                    unsigned char *out = slab + obuf * SLAB_BYTES;
+                    const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + col0 + ch * 64);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint32_t *src = q < 4 ? &r0[8 * q] : &r1[8 * (q - 4)];
+                        const float4 ba = __ldg(b4 + 2 * q), bb = __ldg(b4 + 2 * q + 1);
+                        float v[8] = {__uint_as_float(src[0]) + ba.x, __uint_as_float(src[1]) + ba.y,
+                                      __uint_as_float(src[2]) + ba.z, __uint_as_float(src[3]) + ba.w,
+                                      __uint_as_float(src[4]) + bb.x, __uint_as_float(src[5]) + bb.y,
+                                      __uint_as_float(src[6]) + bb.z, __uint_as_float(src[7]) + bb.w};
+                        if (EPI == VG_EPI_BIAS_QGELU_BF16) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = quick_gelu(v[j]);
+                        }
+                        *reinterpret_cast<uint4 *>(out + slab_off(lane, q)) =
+                            make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+                                       pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                    }
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::tma_store_2d(&tma_out, out, col0 + ch * 64, row0);
+                        ptx::tma_store_commit();
+                    }
+                    obuf ^= 1;
+                }
+            }
+            // accumulator stage drained: tell the leader's MMA warp (one arrival per warp)
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_remote(&tmem_empty[as], 0);
+            if (++as == ACC_STAGES) { as = 0; aphase ^= 1u; }
+        }
+        if (lane == 0) ptx::tma_store_wait_all<0>();
+    }
+
+    ptx::tc_fence_before();
+    __syncwarp();
+    ptx::cluster_sync_all();     // nobody may still touch the peer's smem / TMEM / barriers
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc_pair(tmem_base, ACC_STAGES * BN);
+    }
+}
+
+int make_tmap(VgHandle *h, CUtensorMap *map, CUtensorMapDataType dt, int elt_bytes, const void *ptr,
+              uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols)
+{
+    auto encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(h->tma_encode);
+    if (!encode) {
+        VG_SET_ERR(h, "cuTensorMapEncodeTiled entry point unavailable");
+        return VG_ECUDA;
+    }
+    const cuuint64_t gdim[2] = {cols, rows};
+    const cuuint64_t gstride[1] = {cols * (uint64_t)elt_bytes};
+    const cuuint32_t box[2] = {box_cols, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(map, dt, 2, const_cast<void *>(ptr), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        VG_SET_ERR(h, "cuTensorMapEncodeTiled failed (CUresult %d) rows=%llu cols=%llu", (int)r,
+                   (unsigned long long)rows, (unsigned long long)cols);
+        return VG_ECUDA;
+    }
+    return VG_OK;
+}
+
+template <int EPI>
+int launch_t(VgHandle *h, const GemmArgs &g, cudaStream_t st)
+{
+    CUtensorMap ta, tb, to;
+    int rc = make_tmap(h, &ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.a, (uint64_t)g.M, (uint64_t)g.K,
+                       BM, BK);
+    if (rc) return rc;
+    rc = make_tmap(h, &tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.w, (uint64_t)g.N, (uint64_t)g.K,
+                   BN / 2, BK);
+    if (rc) return rc;
+    if (EPI == VG_EPI_BIAS_RESID_F32)
+        rc = make_tmap(h, &to, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.out, (uint64_t)g.M, (uint64_t)g.N,
+                       32, 32);
+    else
+        rc = make_tmap(h, &to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.out, (uint64_t)g.M,
+                       (uint64_t)g.N, 32, 64);
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VG_CUDA_CHECK(h, cudaFuncSetAttribute(gemm2_kernel<EPI>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)SMEM_BYTES));
+        attr_set = true;
+    }
+    Params p{g.bias, g.M, g.N, g.K};
+    const int64_t tiles = ((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / BN);
+    const int max_clusters = h->num_sms / 2;
+    const int clusters = (int)(tiles < max_clusters ? tiles : max_clusters);
+    const int kind = EPI == VG_EPI_BIAS_BF16 ? VG_K_GEMM_QKV
+                     : EPI == VG_EPI_BIAS_QGELU_BF16 ? VG_K_GEMM_FC
+                     : (g.K == kMlp ? VG_K_GEMM_PROJ : VG_K_GEMM_OUT);
+    VgProfScope prof(h, kind, 2.0 * (double)g.M * g.N * (double)g.K, st);
+    gemm2_kernel<EPI><<<2 * clusters, THREADS, SMEM_BYTES, st>>>(ta, tb, to, p);
+    VG_LAUNCH_CHECK(h);
+    return VG_OK;
+}
+
+}  // namespace
+
+int launch_gemm_2cta(VgHandle *h, const GemmArgs &g, cudaStream_t st)
+{
+    switch (g.epilogue) {
+        case VG_EPI_BIAS_BF16: return launch_t<VG_EPI_BIAS_BF16>(h, g, st);
+        case VG_EPI_BIAS_QGELU_BF16: return launch_t<VG_EPI_BIAS_QGELU_BF16>(h, g, st);
+        case VG_EPI_BIAS_RESID_F32: return launch_t<VG_EPI_BIAS_RESID_F32>(h, g, st);
+    }
+    VG_SET_ERR(h, "gemm2: unsupported epilogue %d", g.epilogue);
+    return VG_EINVAL;
+}
+
+}  // namespace vg
