@@ -112,6 +112,10 @@ int vg_create(const VgConfig *cfg, VgHandle **out)
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) ==
             cudaSuccess && qres == cudaDriverEntryPointSuccess)
         h->tma_encode = fn;
+    if (projection_init(h) != VG_OK) {
+        delete h;
+        return VG_ECUDA;
+    }
     *out = h;
     return VG_OK;
 }
@@ -120,6 +124,7 @@ void vg_destroy(VgHandle *h)
 {
     if (!h) return;
     if (h->arena) cudaFree(h->arena);
+    if (h->proj_tables) cudaFree(h->proj_tables);
     if (h->d_text) cudaFree(h->d_text);
     if (h->d_class_map) cudaFree(h->d_class_map);
     for (auto &r : h->prof) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }

@@ -64,6 +64,7 @@ struct VgHandle {
     void *arena = nullptr;          // one device allocation holding all converted weights
     size_t arena_bytes = 0;
     void *tma_encode = nullptr;     // cuTensorMapEncodeTiled entry point
+    void *proj_tables = nullptr;    // bilinear tables + background tile (projection.cu)
 };
 
 #define VG_SET_ERR(h, ...)                                   \
@@ -117,6 +118,7 @@ struct VgProfScope {
 // kernel launchers implemented in the .cu files ------------------------------------------------
 namespace vg {
 
+int projection_init(VgHandle *h);   // builds the handle-owned projection tables (vg_create)
 int launch_projection(VgHandle *h, const float *d_points, const int32_t *d_offsets, int32_t C,
                       __nv_bfloat16 *d_tiles, uint8_t *d_u8, int32_t *d_status,
                       const VgProjectDebug *dbg, cudaStream_t st);

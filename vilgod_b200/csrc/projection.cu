@@ -32,12 +32,23 @@ constexpr int S = 224;          // output image size
 constexpr int Q = R - 2;        // densified image size (110)
 constexpr int NT = 512;         // threads per CTA
 constexpr int NW = NT / 32;     // 16 warps
-constexpr int ROWS_PER_WARP = R / NW;  // 7
+constexpr int CH = 7;           // rows per warp chunk in the stencil passes (16 x 7 = 112)
 constexpr int HI_ROWS = 56;     // source rows whose horizontal interpolation fits the grid buffer
+constexpr int CAP = 1408;       // points whose quantised (cell, slice, value) are cached in smem
+
+// bilinear index / weight table (identical for rows and columns: square images) and the image a
+// cluster-free region produces, both built once per handle by projection_tables_kernel
+struct ProjTables {
+    int i0[S];
+    float l0[S], l1[S];
+    uint4 bg_tile[VG_TILE_ELEMS * 2 / 16];
+    uint2 bg_u8[S * S / 8];
+};
 
 struct ProjParams {
     const float *points;
     const int32_t *offsets;
+    const ProjTables *tab;
     int32_t C, V;
     float rot[VG_MAX_VIEWS * 9];
     float gauss[9];
@@ -53,12 +64,52 @@ struct ProjParams {
 struct Smem {
     float G[R * R];        // one depth slice of the grid / pooled slice / HI rows (56 x 224)
     float IMG[R * R];      // running max over depth of the smoothed slices, row stride R
+    uint2 cache[CAP];      // per point: (cell | slice << 16, value bits)
     float red[6 * NW];
     float norm[4];         // pcent xyz, prange
     float mx;
+    unsigned rowmask[D][4];   // occupied grid rows per depth slice
+    int ylo[D], yhi[D];
+    int ulo, uhi;          // rows of IMG any slice can touch
     unsigned mask;         // occupied depth slices
     int degenerate;
 };
+
+using f32x2 = unsigned long long;   // two packed fp32 (FFMA2 / FMUL2 / FADD2 on sm_100)
+__device__ __forceinline__ f32x2 pack2(float a, float b)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &a, float &b)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2_rz(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 
 __device__ __forceinline__ void rotate_point(const float *__restrict__ p, const float *rm,
                                              bool fused, float &qx, float &qy, float &qz)
@@ -75,25 +126,42 @@ __device__ __forceinline__ void rotate_point(const float *__restrict__ p, const 
     }
 }
 
-// mv_utils.py:101-118, one rounded op per operator (SURVEY.md appendix A)
-__device__ __forceinline__ void quantise(float qx, float qy, float qz, const float *nm,
-                                         const ProjParams &P, int &cell, int &zi, float &val)
+// Correctly rounded a / b from the correctly rounded reciprocal rcb = RN(1/b):
+//   q = RN(a * rcb);  r = a - b*q (exact, one FMA);  a/b = RN(q + r * rcb)      [Markstein]
+// Bit-identical to IEEE division for normal operands (checked against 2e8 random and adversarial
+// pairs in the ranges used here); `slow` falls back to __fdiv_rn for extreme denominators.  The
+// plain `/` costs ~10 instructions plus a ~30-instruction subroutine whenever the numerator is 0,
+// which is 69 % of the pixels of a depth image.
+__device__ __forceinline__ float div_rn(float a, float b, float rcb, bool slow)
 {
-    const float pr = nm[3];
-    float ux = __fmul_rn(__fdiv_rn(__fsub_rn(qx, nm[0]), pr), 2.0f);
-    float uy = __fmul_rn(__fdiv_rn(__fsub_rn(qy, nm[1]), pr), 2.0f);
-    float uz = __fmul_rn(__fdiv_rn(__fsub_rn(qz, nm[2]), pr), 2.0f);
+    if (slow) return __fdiv_rn(a, b);
+    const float q = __fmul_rn(a, rcb);
+    const float r = __fmaf_rn(-b, q, a);
+    return __fmaf_rn(r, rcb, q);
+}
+
+struct Quant {
+    float cx, cy, cz, pr, rc_pr, rc_opb;
+    bool slow;
+};
+
+// mv_utils.py:101-118, one rounded op per operator (SURVEY.md appendix A)
+__device__ __forceinline__ void quantise(float qx, float qy, float qz, const Quant &n,
+                                         const ProjParams &P, int &X, int &Y, int &zi, float &val)
+{
+    float ux = __fmul_rn(div_rn(__fsub_rn(qx, n.cx), n.pr, n.rc_pr, n.slow), 2.0f);
+    float uy = __fmul_rn(div_rn(__fsub_rn(qy, n.cy), n.pr, n.rc_pr, n.slow), 2.0f);
+    float uz = __fmul_rn(div_rn(__fsub_rn(qz, n.cz), n.pr, n.rc_pr, n.slow), 2.0f);
     ux = __fmul_rn(ux, P.obj_ratio);
     uy = __fmul_rn(uy, P.obj_ratio);
     const float fx = __fmul_rn(__fmul_rn(__fadd_rn(ux, 1.0f), 0.5f), (float)R);
     const float fy = __fmul_rn(__fmul_rn(__fadd_rn(uy, 1.0f), 0.5f), (float)R);
     float fz = __fadd_rn(__fmul_rn(__fadd_rn(uz, 1.0f), 0.5f), P.depth_bias);
-    fz = __fmul_rn(__fdiv_rn(fz, P.one_plus_bias), (float)(D - 2));
-    const float X = fminf(fmaxf(ceilf(fx), 1.0f), (float)(R - 2));
-    const float Y = fminf(fmaxf(ceilf(fy), 1.0f), (float)(R - 2));
-    zi = (int)ceilf(fz);
+    fz = __fmul_rn(div_rn(fz, P.one_plus_bias, n.rc_opb, n.slow), (float)(D - 2));
+    X = (int)fminf(fmaxf(ceilf(fx), 1.0f), (float)(R - 2));
+    Y = (int)fminf(fmaxf(ceilf(fy), 1.0f), (float)(R - 2));
+    zi = min(max((int)ceilf(fz), 0), D - 1);
     val = fminf(fmaxf(fz, 1.0f), (float)(D - 2));
-    cell = (int)Y * R + (int)X;
 }
 
 __device__ __forceinline__ float warp_max(float v)
@@ -108,7 +176,6 @@ __device__ __forceinline__ float warp_min(float v)
     for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-
 __device__ __forceinline__ float4 max4(float4 a, float4 b)
 {
     return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
@@ -126,6 +193,37 @@ __device__ __forceinline__ void lin_idx(int dst, int &i0, float &l0, float &l1)
     i0 = a;
     l1 = lam;
     l0 = __fsub_rn(1.0f, lam);
+}
+
+// floor(o * 255) for o in [0, 1] as an exact float: np.uint8(x*255) truncates; 2^23 + s rounded
+// toward zero leaves floor(s) in the low mantissa bits, subtracting 2^23 gives it back.
+__device__ __forceinline__ float quant255(float o)
+{
+    const float t = __fadd_rz(__fmul_rn(o, 255.0f), 8388608.0f);
+    return __fsub_rn(t, 8388608.0f);
+}
+
+__global__ void projection_tables_kernel(ProjTables *t)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid < S) {
+        int i0; float l0, l1;
+        lin_idx(tid, i0, l0, l1);
+        t->i0[tid] = i0; t->l0[tid] = l0; t->l1[tid] = l1;
+    }
+    // the image of an all-background (1.0) neighbourhood: HI = fma(1, lw0, 1*lw1), then the
+    // vertical pass -- 254 or 255 depending on how (w0 + w1) rounds, exactly like torch-CPU
+    for (int px = tid; px < S * S; px += gridDim.x * blockDim.x) {
+        const int oy = px / S, ox = px - oy * S;
+        int x0, y0; float lw0, lw1, lh0, lh1;
+        lin_idx(ox, x0, lw0, lw1);
+        lin_idx(oy, y0, lh0, lh1);
+        const float c = __fmaf_rn(1.0f, lw0, __fmul_rn(1.0f, lw1));
+        const float v = quant255(__fmaf_rn(c, lh0, __fmul_rn(c, lh1)));
+        reinterpret_cast<uint8_t *>(t->bg_u8)[px] = (uint8_t)v;
+        const int patch = (oy >> 4) * 14 + (ox >> 4), inner = (oy & 15) * 16 + (ox & 15);
+        reinterpret_cast<__nv_bfloat16 *>(t->bg_tile)[patch * 256 + inner] = __float2bfloat16_rn(v);
+    }
 }
 
 __global__ void __launch_bounds__(NT, 2) projection_kernel(const ProjParams P)
@@ -156,6 +254,7 @@ __global__ void __launch_bounds__(NT, 2) projection_kernel(const ProjParams P)
     mx0 = warp_max(mx0); mx1 = warp_max(mx1); mx2 = warp_max(mx2);
     mn0 = warp_min(mn0); mn1 = warp_min(mn1); mn2 = warp_min(mn2);
     const bool all_finite = __all_sync(0xffffffffu, finite);
+    if (tid < D * 4) (&sm.rowmask[0][0])[tid] = 0u;
     if (tid == 0) { sm.mask = 0u; sm.degenerate = 0; }
     __syncthreads();
     if (lane == 0) {
@@ -195,31 +294,66 @@ __global__ void __launch_bounds__(NT, 2) projection_kernel(const ProjParams P)
         return;
     }
     if (P.status && v == 0 && tid == 0) P.status[c] = VG_OK;
-    const float nm[4] = {sm.norm[0], sm.norm[1], sm.norm[2], sm.norm[3]};
+    Quant qn;
+    qn.cx = sm.norm[0]; qn.cy = sm.norm[1]; qn.cz = sm.norm[2]; qn.pr = sm.norm[3];
+    qn.rc_pr = __frcp_rn(qn.pr);
+    qn.rc_opb = __frcp_rn(P.one_plus_bias);
+    qn.slow = !(qn.pr > 1e-18f && qn.pr < 1e18f);
 
-    // ---- phase 2: which depth slices are occupied ------------------------------------------------
+    // ---- phase 2: quantise once; occupied slices and rows; cache (cell, slice, value) ------------
     {
         unsigned m = 0u;
         for (int i = tid; i < n; i += NT) {
-            float qx, qy, qz, val; int cell, zi;
+            float qx, qy, qz, val; int X, Y, zi;
             rotate_point(pts + 3 * i, rm, fused, qx, qy, qz);
-            quantise(qx, qy, qz, nm, P, cell, zi, val);
-            m |= 1u << (zi & 31);
+            quantise(qx, qy, qz, qn, P, X, Y, zi, val);
+            m |= 1u << zi;
+            atomicOr(&sm.rowmask[zi][Y >> 5], 1u << (Y & 31));
+            if (i < CAP) sm.cache[i] = make_uint2((unsigned)(Y * R + X) | ((unsigned)zi << 16),
+                                                  __float_as_uint(val));
         }
         m = __reduce_or_sync(0xffffffffu, m);
         if (lane == 0 && m) atomicOr(&sm.mask, m);
     }
-    // IMG starts at 0 == max over the empty slices (their smoothed image is identically 0)
-    for (int i = tid; i < R * R / 4; i += NT)
-        reinterpret_cast<float4 *>(sm.IMG)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
-    const unsigned mask = sm.mask & ((1u << D) - 1u);
+    if (tid < D) {
+        int lo = R, hi = -1;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const unsigned bits = sm.rowmask[tid][w];
+            if (bits) {
+                lo = min(lo, 32 * w + __ffs(bits) - 1);
+                hi = max(hi, 32 * w + 31 - __clz(bits));
+            }
+        }
+        sm.ylo[tid] = lo; sm.yhi[tid] = hi;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int ulo = Q, uhi = -1;
+        for (int d = 0; d < D; ++d)
+            if (sm.yhi[d] >= 0) {
+                ulo = min(ulo, max(sm.ylo[d] - 4, 0));
+                uhi = max(uhi, min(sm.yhi[d] + 2, Q - 1));
+            }
+        sm.ulo = ulo; sm.uhi = uhi;
+    }
+    __syncthreads();
+    const unsigned mask = sm.mask;
+    const int ulo = sm.ulo, uhi = sm.uhi;                 // IMG rows any slice writes
+    const int nlo = max(ulo - 1, 0), nhi = min(uhi + 1, Q - 1);   // rows the emit may read
+    // IMG starts at 0 == max over the empty slices (their smoothed image is identically 0)
+    for (int i = tid; i < (nhi - nlo + 1) * (R / 4); i += NT)
+        reinterpret_cast<float4 *>(sm.IMG + nlo * R)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     float w[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) w[k] = P.gauss[k];
 
     // ---- phase 3: per occupied slice: scatter-max, 5x5 max-pool, 3x3 Gaussian, depth max --------
+    // Only the rows a slice can influence are touched: points in rows [ylo, yhi] spread to pooled
+    // rows [ylo-3, yhi+1] and smoothed rows [ylo-4, yhi+2]; the band [ylo-5, yhi+4] is cleared so
+    // every halo row the stencils read is zero.  Stale rows outside the band are never read.
     for (int d = 0; d < D; ++d) {
         if (!((mask >> d) & 1u)) {
             if (P.dbg_grid) {
@@ -228,26 +362,38 @@ __global__ void __launch_bounds__(NT, 2) projection_kernel(const ProjParams P)
             }
             continue;
         }
-        for (int i = tid; i < R * R / 4; i += NT)
-            reinterpret_cast<float4 *>(sm.G)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int ylo = sm.ylo[d], yhi = sm.yhi[d];
+        const int blo = max(ylo - 5, 0), bhi = min(yhi + 4, R - 1);
+        for (int i = tid; i < (bhi - blo + 1) * (R / 4); i += NT)
+            reinterpret_cast<float4 *>(sm.G + blo * R)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
-        for (int i = tid; i < n; i += NT) {
-            float qx, qy, qz, val; int cell, zi;
-            rotate_point(pts + 3 * i, rm, fused, qx, qy, qz);
-            quantise(qx, qy, qz, nm, P, cell, zi, val);
-            // all values are positive floats: integer order == float order
-            if (zi == d) atomicMax(reinterpret_cast<int *>(sm.G) + cell, __float_as_int(val));
+        {
+            const int ncache = min(n, CAP);
+            for (int i = tid; i < ncache; i += NT) {
+                const uint2 e = sm.cache[i];
+                // all values are positive floats: integer order == float order
+                if ((int)(e.x >> 16) == d)
+                    atomicMax(reinterpret_cast<int *>(sm.G) + (e.x & 0xffffu), (int)e.y);
+            }
+            for (int i = CAP + tid; i < n; i += NT) {
+                float qx, qy, qz, val; int X, Y, zi;
+                rotate_point(pts + 3 * i, rm, fused, qx, qy, qz);
+                quantise(qx, qy, qz, qn, P, X, Y, zi, val);
+                if (zi == d) atomicMax(reinterpret_cast<int *>(sm.G) + Y * R + X, __float_as_int(val));
+            }
         }
         __syncthreads();
         if (P.dbg_grid) {
             float *g = P.dbg_grid + ((size_t)b * D + d) * R * R;
-            for (int i = tid; i < R * R; i += NT) g[i] = sm.G[i];
+            for (int i = tid; i < R * R; i += NT) {
+                const int y = i / R;
+                g[i] = (y >= blo && y <= bhi) ? sm.G[i] : 0.0f;
+            }
             __syncthreads();
         }
 
         // horizontal 5-max in place, one warp per row: H(y,x) = max G(y, x-1..x+3), x in [0,110)
-        for (int r = 0; r < ROWS_PER_WARP; ++r) {
-            const int y = warp * ROWS_PER_WARP + r;
+        for (int y = ylo + warp; y <= yhi; y += NW) {
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
             if (lane < R / 4) a = reinterpret_cast<const float4 *>(sm.G + y * R)[lane];
             const float left = __shfl_up_sync(0xffffffffu, a.w, 1);
@@ -271,22 +417,23 @@ __global__ void __launch_bounds__(NT, 2) projection_kernel(const ProjParams P)
         // vertical 5-max in place: warp = 7-row chunk, lane = 4-column group.
         // P(y,x) = max H(y-1..y+3, x); all loads precede all stores (barrier in between).
         {
-            const int y0 = warp * ROWS_PER_WARP;
-            float4 h[ROWS_PER_WARP + 4];
+            const int vlo = max(ylo - 3, 0), vhi = min(yhi + 1, R - 1);
+            const int y0 = vlo + warp * CH;
+            float4 h[CH + 4];
 #pragma unroll
-            for (int k = 0; k < ROWS_PER_WARP + 4; ++k) {
+            for (int k = 0; k < CH + 4; ++k) {
                 const int y = y0 - 1 + k;
                 h[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (lane < R / 4 && y >= 0 && y < R)
+                if (lane < R / 4 && y0 <= vhi && y >= 0 && y < R)
                     h[k] = reinterpret_cast<const float4 *>(sm.G + y * R)[lane];
             }
             __syncthreads();
 #pragma unroll
-            for (int k = 0; k < ROWS_PER_WARP; ++k) {
+            for (int k = 0; k < CH; ++k) {
                 const int y = y0 + k;
                 float4 o = max4(max4(max4(h[k], h[k + 1]), max4(h[k + 2], h[k + 3])), h[k + 4]);
                 if (y >= Q) o = make_float4(0.f, 0.f, 0.f, 0.f);   // rows 110, 111: padding
-                if (lane < R / 4) reinterpret_cast<float4 *>(sm.G + y * R)[lane] = o;
+                if (lane < R / 4 && y <= vhi) reinterpret_cast<float4 *>(sm.G + y * R)[lane] = o;
             }
         }
         __syncthreads();
@@ -294,57 +441,61 @@ __global__ void __launch_bounds__(NT, 2) projection_kernel(const ProjParams P)
         // 3x3 Gaussian (zero padding) and running max over depth into IMG.
         // acc = fma(w[i][j], P(y+i-1, x+j-1), acc) in row-major tap order.
         {
-            const int y0 = warp * ROWS_PER_WARP;
-            float4 pa, pb, pc;          // rows y-1, y, y+1
-            float la, lb, lc, ra, rb, rc;
-            auto load_row = [&](int y, float4 &p, float &l, float &r) {
-                p = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (lane < R / 4 && y >= 0 && y < Q)
-                    p = reinterpret_cast<const float4 *>(sm.G + y * R)[lane];
-                l = __shfl_up_sync(0xffffffffu, p.w, 1);
-                r = __shfl_down_sync(0xffffffffu, p.x, 1);
-                if (lane == 0) l = 0.0f;
-            };
-            load_row(y0 - 1, pa, la, ra);
-            load_row(y0, pb, lb, rb);
+            const int glo = max(ylo - 4, 0), ghi = min(yhi + 2, Q - 1);
+            const int y0 = glo + warp * CH;
+            if (y0 <= ghi) {
+                float4 pa, pb, pc;          // rows y-1, y, y+1
+                float la, lb, lc, ra, rb, rc;
+                auto load_row = [&](int y, float4 &p, float &l, float &r) {
+                    p = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (lane < R / 4 && y >= 0 && y < Q)
+                        p = reinterpret_cast<const float4 *>(sm.G + y * R)[lane];
+                    l = __shfl_up_sync(0xffffffffu, p.w, 1);
+                    r = __shfl_down_sync(0xffffffffu, p.x, 1);
+                    if (lane == 0) l = 0.0f;
+                };
+                load_row(y0 - 1, pa, la, ra);
+                load_row(y0, pb, lb, rb);
 #pragma unroll
-            for (int k = 0; k < ROWS_PER_WARP; ++k) {
-                const int y = y0 + k;
-                load_row(y + 1, pc, lc, rc);
-                const float ta[6] = {la, pa.x, pa.y, pa.z, pa.w, ra};
-                const float tb[6] = {lb, pb.x, pb.y, pb.z, pb.w, rb};
-                const float tc[6] = {lc, pc.x, pc.y, pc.z, pc.w, rc};
-                float o[4];
+                for (int k = 0; k < CH; ++k) {
+                    const int y = y0 + k;
+                    if (y > ghi) break;        // warp-uniform
+                    load_row(y + 1, pc, lc, rc);
+                    const float ta[6] = {la, pa.x, pa.y, pa.z, pa.w, ra};
+                    const float tb[6] = {lb, pb.x, pb.y, pb.z, pb.w, rb};
+                    const float tc[6] = {lc, pc.x, pc.y, pc.z, pc.w, rc};
+                    float o[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float acc = __fmul_rn(w[0], ta[j]);
-                    acc = __fmaf_rn(w[1], ta[j + 1], acc);
-                    acc = __fmaf_rn(w[2], ta[j + 2], acc);
-                    acc = __fmaf_rn(w[3], tb[j], acc);
-                    acc = __fmaf_rn(w[4], tb[j + 1], acc);
-                    acc = __fmaf_rn(w[5], tb[j + 2], acc);
-                    acc = __fmaf_rn(w[6], tc[j], acc);
-                    acc = __fmaf_rn(w[7], tc[j + 1], acc);
-                    acc = __fmaf_rn(w[8], tc[j + 2], acc);
-                    o[j] = acc;
+                    for (int j = 0; j < 4; ++j) {
+                        float acc = __fmul_rn(w[0], ta[j]);
+                        acc = __fmaf_rn(w[1], ta[j + 1], acc);
+                        acc = __fmaf_rn(w[2], ta[j + 2], acc);
+                        acc = __fmaf_rn(w[3], tb[j], acc);
+                        acc = __fmaf_rn(w[4], tb[j + 1], acc);
+                        acc = __fmaf_rn(w[5], tb[j + 2], acc);
+                        acc = __fmaf_rn(w[6], tc[j], acc);
+                        acc = __fmaf_rn(w[7], tc[j + 1], acc);
+                        acc = __fmaf_rn(w[8], tc[j + 2], acc);
+                        o[j] = acc;
+                    }
+                    if (lane == R / 4 - 1) { o[2] = 0.0f; o[3] = 0.0f; }
+                    if (lane < R / 4) {
+                        float4 *dst = reinterpret_cast<float4 *>(sm.IMG + y * R) + lane;
+                        *dst = max4(*dst, make_float4(o[0], o[1], o[2], o[3]));
+                    }
+                    pa = pb; la = lb; ra = rb;
+                    pb = pc; lb = lc; rb = rc;
                 }
-                if (lane == R / 4 - 1) { o[2] = 0.0f; o[3] = 0.0f; }
-                if (lane < R / 4 && y < Q) {
-                    float4 *dst = reinterpret_cast<float4 *>(sm.IMG + y * R) + lane;
-                    *dst = max4(*dst, make_float4(o[0], o[1], o[2], o[3]));
-                }
-                pa = pb; la = lb; ra = rb;
-                pb = pc; lb = lc; rb = rc;
             }
         }
         __syncthreads();
     }
 
-    // ---- phase 4: img / max(img), 1 - x ---------------------------------------------------------
+    // ---- phase 4: img / max(img), 1 - x  (rows the emit reads; everything else is background) ----
     {
         float m = 0.0f;
-        for (int i = tid; i < Q * R / 4; i += NT) {
-            const float4 t = reinterpret_cast<const float4 *>(sm.IMG)[i];
+        for (int i = tid; i < (uhi - ulo + 1) * (R / 4); i += NT) {
+            const float4 t = reinterpret_cast<const float4 *>(sm.IMG + ulo * R)[i];
             m = fmaxf(fmaxf(m, fmaxf(t.x, t.y)), fmaxf(t.z, t.w));
         }
         m = warp_max(m);
@@ -357,62 +508,87 @@ __global__ void __launch_bounds__(NT, 2) projection_kernel(const ProjParams P)
         }
         __syncthreads();
         const float mx = sm.mx;
-        for (int i = tid; i < Q * R / 4; i += NT) {
-            float4 t = reinterpret_cast<float4 *>(sm.IMG)[i];
-            t.x = __fsub_rn(1.0f, __fdiv_rn(t.x, mx));
-            t.y = __fsub_rn(1.0f, __fdiv_rn(t.y, mx));
-            t.z = __fsub_rn(1.0f, __fdiv_rn(t.z, mx));
-            t.w = __fsub_rn(1.0f, __fdiv_rn(t.w, mx));
-            reinterpret_cast<float4 *>(sm.IMG)[i] = t;
+        const float rc_mx = __frcp_rn(mx);
+        for (int i = tid; i < (nhi - nlo + 1) * (R / 4); i += NT) {
+            float4 t = reinterpret_cast<float4 *>(sm.IMG + nlo * R)[i];
+            t.x = __fsub_rn(1.0f, div_rn(t.x, mx, rc_mx, false));
+            t.y = __fsub_rn(1.0f, div_rn(t.y, mx, rc_mx, false));
+            t.z = __fsub_rn(1.0f, div_rn(t.z, mx, rc_mx, false));
+            t.w = __fsub_rn(1.0f, div_rn(t.w, mx, rc_mx, false));
+            reinterpret_cast<float4 *>(sm.IMG + nlo * R)[i] = t;
         }
         __syncthreads();
         if (P.dbg_dens) {
             float *dd = P.dbg_dens + (size_t)b * Q * Q;
-            for (int i = tid; i < Q * Q; i += NT) dd[i] = sm.IMG[(i / Q) * R + (i % Q)];
+            for (int i = tid; i < Q * Q; i += NT) {
+                const int y = i / Q;
+                dd[i] = (y >= nlo && y <= nhi) ? sm.IMG[y * R + (i - y * Q)] : 1.0f;
+            }
         }
     }
 
     // ---- phase 5: bilinear 110 -> 224 (align_corners), floor(x*255), patch-major bf16 tiles ------
     // Two halves: HI[y][ox] = fma(IMG[y][x0], lw0, IMG[y][x1]*lw1) for 56 source rows at a time
     // (held in the grid buffer), then out = fma(HI[y0], lh0, HI[y1]*lh1) -- the exact contraction
-    // pattern of torch-CPU's separable interpolation on an FMA host.
+    // pattern of torch-CPU's separable interpolation on an FMA host.  One warp per output row; rows
+    // whose two source rows lie outside [ulo, uhi] are copied from the precomputed background tile.
     __nv_bfloat16 *tile = P.tiles ? P.tiles + (size_t)b * VG_TILE_ELEMS : nullptr;
     uint8_t *u8 = P.u8 ? P.u8 + (size_t)b * S * S : nullptr;
+    const ProjTables *__restrict__ tab = P.tab;
+    int cx0 = 0, cx1 = 0;
+    float clw0 = 0.f, clw1 = 0.f;
+    if (tid < 2 * S) {
+        const int ox = tid % S;
+        cx0 = __ldg(&tab->i0[ox]);
+        clw0 = __ldg(&tab->l0[ox]);
+        clw1 = __ldg(&tab->l1[ox]);
+        cx1 = cx0 + (cx0 < Q - 1 ? 1 : 0);
+    }
+    const f32x2 k255 = pack2(255.0f, 255.0f), kmagic = pack2(8388608.0f, 8388608.0f);
     for (int half = 0; half < 2; ++half) {
         const int ybase = half == 0 ? 0 : Q - HI_ROWS + 1;        // source rows 0..55 / 55..109
         const int nrows = half == 0 ? HI_ROWS : Q - ybase;        // 56 / 55
         const int oy_beg = half == 0 ? 0 : 113, oy_end = half == 0 ? 113 : S;
         if (tid < 2 * S) {
-            const int ox = tid % S, rsel = tid / S;
-            int x0; float lw0, lw1;
-            lin_idx(ox, x0, lw0, lw1);
-            const int x1 = x0 + (x0 < Q - 1 ? 1 : 0);
-            for (int r = rsel; r < nrows; r += 2) {
-                const float *row = sm.IMG + (ybase + r) * R;
-                sm.G[r * S + ox] = __fmaf_rn(row[x0], lw0, __fmul_rn(row[x1], lw1));
+            const int ox = tid % S;
+            const int r_lo = max(nlo, ybase), r_hi = min(nhi, ybase + nrows - 1);
+            for (int y = r_lo + tid / S; y <= r_hi; y += 2) {
+                const float *row = sm.IMG + y * R;
+                sm.G[(y - ybase) * S + ox] = __fmaf_rn(row[cx0], clw0, __fmul_rn(row[cx1], clw1));
             }
         }
         __syncthreads();
-        const int items = (oy_end - oy_beg) * (S / 8);
-        for (int it = tid; it < items; it += NT) {
-            const int oy = oy_beg + it / (S / 8), g = it % (S / 8);
-            int y0; float lh0, lh1;
-            lin_idx(oy, y0, lh0, lh1);
+        for (int oy = oy_beg + warp; oy < oy_end; oy += NW) {
+            const int y0 = __ldg(&tab->i0[oy]);
             const int y1 = y0 + (y0 < Q - 1 ? 1 : 0);
-            const float4 *r0 = reinterpret_cast<const float4 *>(sm.G + (y0 - ybase) * S + 8 * g);
-            const float4 *r1 = reinterpret_cast<const float4 *>(sm.G + (y1 - ybase) * S + 8 * g);
-            const float4 a0 = r0[0], a1 = r0[1], b0 = r1[0], b1 = r1[1];
-            const float ta[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const float tb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            if (lane >= S / 8) continue;
+            const int g = lane;
+            const int patch = (oy >> 4) * 14 + (g >> 1);
+            const int inner = (oy & 15) * 16 + (g & 1) * 8;
+            if (y1 < ulo || y0 > uhi) {            // warp-uniform: pure background row
+                if (tile)
+                    *reinterpret_cast<uint4 *>(tile + patch * 256 + inner) =
+                        __ldg(&tab->bg_tile[(patch * 256 + inner) >> 3]);
+                if (u8)
+                    *reinterpret_cast<uint2 *>(u8 + oy * S + 8 * g) = __ldg(&tab->bg_u8[(oy * S + 8 * g) >> 3]);
+                continue;
+            }
+            const float lh0 = __ldg(&tab->l0[oy]), lh1 = __ldg(&tab->l1[oy]);
+            const f32x2 h0 = pack2(lh0, lh0), h1 = pack2(lh1, lh1);
+            const ulonglong2 *r0 = reinterpret_cast<const ulonglong2 *>(sm.G + (y0 - ybase) * S + 8 * g);
+            const ulonglong2 *r1 = reinterpret_cast<const ulonglong2 *>(sm.G + (y1 - ybase) * S + 8 * g);
+            const ulonglong2 a0 = r0[0], a1 = r0[1], b0 = r1[0], b1 = r1[1];
+            const f32x2 ta[4] = {a0.x, a0.y, a1.x, a1.y};
+            const f32x2 tb[4] = {b0.x, b0.y, b1.x, b1.y};
             unsigned fb[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float o = __fmaf_rn(ta[j], lh0, __fmul_rn(tb[j], lh1));
-                const float s255 = __fmul_rn(o, 255.0f);
-                // np.uint8(x*255): truncation.  2^23 + s rounded toward zero leaves floor(s) in
-                // the low mantissa bits; subtracting 2^23 gives it back as an exact float.
-                const float t = __fadd_rz(s255, 8388608.0f);
-                fb[j] = __float_as_uint(__fsub_rn(t, 8388608.0f));
+            for (int j = 0; j < 4; ++j) {
+                const f32x2 o = fma2(ta[j], h0, mul2(tb[j], h1));
+                const f32x2 q = sub2(add2_rz(mul2(o, k255), kmagic), kmagic);
+                float q0, q1;
+                unpack2(q, q0, q1);
+                fb[2 * j] = __float_as_uint(q0);
+                fb[2 * j + 1] = __float_as_uint(q1);
             }
             if (tile) {
                 // integers 0..255 are exact in bf16: the bf16 pattern is the high half of the fp32
@@ -421,8 +597,6 @@ __global__ void __launch_bounds__(NT, 2) projection_kernel(const ProjParams P)
                 pk.y = __byte_perm(fb[2], fb[3], 0x7632);
                 pk.z = __byte_perm(fb[4], fb[5], 0x7632);
                 pk.w = __byte_perm(fb[6], fb[7], 0x7632);
-                const int patch = (oy >> 4) * 14 + (g >> 1);
-                const int inner = (oy & 15) * 16 + (g & 1) * 8;
                 *reinterpret_cast<uint4 *>(tile + patch * 256 + inner) = pk;
             }
             if (u8) {
@@ -441,6 +615,20 @@ __global__ void __launch_bounds__(NT, 2) projection_kernel(const ProjParams P)
 
 }  // namespace
 
+int projection_init(VgHandle *h)
+{
+    ProjTables *t = nullptr;
+    VG_CUDA_CHECK(h, cudaMalloc(&t, sizeof(ProjTables)));
+    projection_tables_kernel<<<64, 256>>>(t);
+    VG_CUDA_CHECK(h, cudaGetLastError());
+    VG_CUDA_CHECK(h, cudaDeviceSynchronize());
+    VG_CUDA_CHECK(h, cudaFuncSetAttribute(projection_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(Smem)));
+    h->proj_tables = t;
+    return VG_OK;
+}
+
 int launch_projection(VgHandle *h, const float *d_points, const int32_t *d_offsets, int32_t C,
                       __nv_bfloat16 *d_tiles, uint8_t *d_u8, int32_t *d_status,
                       const VgProjectDebug *dbg, cudaStream_t st)
@@ -455,6 +643,7 @@ int launch_projection(VgHandle *h, const float *d_points, const int32_t *d_offse
     ProjParams P;
     P.points = d_points;
     P.offsets = d_offsets;
+    P.tab = static_cast<const ProjTables *>(h->proj_tables);
     P.C = C;
     P.V = cfg.num_views;
     memcpy(P.rot, cfg.rot, sizeof(P.rot));
@@ -468,13 +657,6 @@ int launch_projection(VgHandle *h, const float *d_points, const int32_t *d_offse
     P.status = d_status;
     P.dbg_grid = dbg ? dbg->d_grid : nullptr;
     P.dbg_dens = dbg ? dbg->d_densified : nullptr;
-    static bool attr_set = false;
-    if (!attr_set) {
-        VG_CUDA_CHECK(h, cudaFuncSetAttribute(projection_kernel,
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)sizeof(Smem)));
-        attr_set = true;
-    }
     const long long blocks = (long long)C * cfg.num_views;
     // algorithmic bytes recorded here: the emitted tiles; the caller adds 12 * sum(N) for the points
     VgProfScope prof(h, VG_K_PROJECTION, (double)blocks * VG_TILE_ELEMS * 2.0, st);
