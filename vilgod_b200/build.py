@@ -12,6 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(OUT_DIR, "libvilgod_b200.so")
 SOURCES = ["api.cu", "projection.cu", "gemm_tcgen05.cu", "gemm_tcgen05_2cta.cu", "attention.cu",
+           "attention_tcgen05.cu",
            "vit_misc.cu"]
 HEADERS = ["common.cuh", "ptx.cuh", os.path.join("..", "..", "include", "vilgod_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

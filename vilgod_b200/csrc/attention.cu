@@ -8,6 +8,8 @@
 // Tensor-core path: register-level mma.sync m16n8k16 bf16 (fp32 accumulate).  Attention is 4 % of
 // the tower's FLOPs; the GEMMs that carry the other 96 % run on tcgen05 (gemm_tcgen05.cu).
 // The 1/sqrt(64) query scale is folded into the in-proj weights at load time (weights.cu).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace vg {
@@ -204,6 +206,9 @@ int launch_attention(VgHandle *h, const __nv_bfloat16 *qkv, int64_t B, __nv_bflo
                      cudaStream_t st)
 {
     if (B <= 0) return VG_OK;
+    // production path: tcgen05 kernel (attention_tcgen05.cu); VG_ATTN_V1=1 selects this mma.sync one
+    static const bool force_v1 = getenv("VG_ATTN_V1") != nullptr;
+    if (!force_v1) return launch_attention_tc(h, qkv, B, out, st);
     static bool attr_set = false;
     if (!attr_set) {
         VG_CUDA_CHECK(h, cudaFuncSetAttribute(attention_kernel,

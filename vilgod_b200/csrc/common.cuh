@@ -139,6 +139,8 @@ int launch_gemm_2cta(VgHandle *h, const GemmArgs &g, cudaStream_t st);   // cta_
 
 int launch_attention(VgHandle *h, const __nv_bfloat16 *qkv, int64_t B, __nv_bfloat16 *out,
                      cudaStream_t st);
+int launch_attention_tc(VgHandle *h, const __nv_bfloat16 *qkv, int64_t B, __nv_bfloat16 *out,
+                        cudaStream_t st);   // tcgen05 / TMEM path (attention_tcgen05.cu)
 int launch_layernorm_bf16(VgHandle *h, const float *x, const float *w, const float *b,
                           int64_t rows, __nv_bfloat16 *y, cudaStream_t st);
 // x[img,0,:] = table[0]; then x = LN(x) in place (ln_pre) over all B*197 rows
