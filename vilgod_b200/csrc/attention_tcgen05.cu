@@ -29,7 +29,7 @@ constexpr int KV_BYTES = LP * 128;            // 26,624
 constexpr int STAGE_BYTES = Q_BYTES + 2 * KV_BYTES;   // 86,016
 constexpr int BOX_BYTES = LP * 128;
 constexpr int STAGES = 2;
-constexpr int THREADS = 384;          // warp 0 TMA, warp 1 MMA, warps 2-3 idle, warps 4-11 softmax
+constexpr int THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2-5 / 6-9 soft-max warpgroups
 constexpr int SLOT_COLS = 256;
 constexpr int O_COL = 128;
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
@@ -75,6 +75,41 @@ __device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&r)[8
 __device__ __forceinline__ void tmem_st_wait()
 {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+using f32x2 = unsigned long long;   // packed pair of fp32 (FFMA2 / FADD2)
+__device__ __forceinline__ f32x2 pack2(float a, float b)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &a, float &b)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ float max3(float a, float b, float c)
+{
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
 {
@@ -156,52 +191,74 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, __nv_bfloat16 *
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
+        // Software-pipelined so that each warpgroup's next S is queued as early as its TMEM slot
+        // allows: ... PV(small, i) -> S(big, i+1) -> PV(big, i) -> S(small, i+1) -> PV(small, i+1) ...
+        // (the slot that held the small block of item i takes the big block of item i+1)
         if (lane == 0) {
             constexpr uint32_t idesc_s = idesc_bf16(128, LP, 0);   // S = Q K^T, both K-major
             constexpr uint32_t idesc_o = idesc_bf16(128, HD, 1);   // O = P V, V is MN-major
+            auto issue_s = [&](uint32_t st, int slot, int blk) {
+                const uint64_t dk = ptx::make_kmajor_sw128_desc(st + Q_BYTES);
+                const uint64_t dq = ptx::make_kmajor_sw128_desc(st + blk * (Q_BYTES / 2));
+                const uint32_t d_s = tmem_base + (uint32_t)(slot * SLOT_COLS);
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k)
+                    ptx::mma_f16_ss(d_s, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s,
+                                    (uint32_t)(k != 0));
+                ptx::tc_commit(&s_full[slot]);
+            };
+            auto issue_pv = [&](uint32_t st, int slot) {
+                const uint32_t a_p = tmem_base + (uint32_t)(slot * SLOT_COLS);
+                const uint32_t d_o = a_p + O_COL;
+#pragma unroll
+                for (int k = 0; k < LP / 16; ++k) {
+                    const uint64_t dv =
+                        make_mnmajor_sw128_desc(st + Q_BYTES + KV_BYTES + (uint32_t)(k * 16 * 128));
+                    mma_f16_ts(d_o, a_p + (uint32_t)(8 * k), dv, idesc_o, (uint32_t)(k != 0));
+                }
+                ptx::tc_commit(&o_full[slot]);
+            };
             int it = 0;
+            if ((int64_t)blockIdx.x < num_items) {      // prologue: both S of the first item
+                const uint32_t st0 = ptx::smem_u32(smem);
+                ptx::mbar_wait(&kv_full[0], 0u);
+                ptx::tc_fence_after();
+                issue_s(st0, 0, 0);
+                issue_s(st0, 1, 1);
+            }
             for (int64_t item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
                 const int s = it & 1;
-                const uint32_t ph = (uint32_t)(it >> 1) & 1u, ip = (uint32_t)it & 1u;
+                const uint32_t ip = (uint32_t)it & 1u;
                 const uint32_t st = ptx::smem_u32(smem + (size_t)s * STAGE_BYTES);
-                ptx::mbar_wait(&kv_full[s], ph);
+                const int small_slot = 1 ^ (int)ip, big_slot = (int)ip;
+                const bool has_next = item + gridDim.x < num_items;
+                const int sn = (it + 1) & 1;
+                const uint32_t phn = (uint32_t)((it + 1) >> 1) & 1u;
+                const uint32_t stn = ptx::smem_u32(smem + (size_t)sn * STAGE_BYTES);
+
+                ptx::mbar_wait(&p_full[small_slot], ip);
                 ptx::tc_fence_after();
-                const uint64_t dk = ptx::make_kmajor_sw128_desc(st + Q_BYTES);
-#pragma unroll
-                for (int slot = 0; slot < 2; ++slot) {
-                    const int blk = slot ^ (int)ip;       // query block this slot handles for this item
-                    ptx::mbar_wait(&slot_free[slot], ip ^ 1u);
+                issue_pv(st, small_slot);
+                if (has_next) {
+                    ptx::mbar_wait(&kv_full[sn], phn);
+                    ptx::mbar_wait(&slot_free[small_slot], ip);   // its O of this item has been read
                     ptx::tc_fence_after();
-                    const uint64_t dq = ptx::make_kmajor_sw128_desc(st + blk * (Q_BYTES / 2));
-                    const uint32_t d_s = tmem_base + (uint32_t)(slot * SLOT_COLS);
-#pragma unroll
-                    for (int k = 0; k < HD / 16; ++k)
-                        ptx::mma_f16_ss(d_s, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s,
-                                        (uint32_t)(k != 0));
-                    ptx::tc_commit(&s_full[slot]);
+                    issue_s(stn, small_slot, 0);
                 }
-                // the slot with the small (69-row) block finishes its soft-max first
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int slot = (j ^ 1) ^ (int)ip;
-                    ptx::mbar_wait(&p_full[slot], ip);
+                ptx::mbar_wait(&p_full[big_slot], ip);
+                ptx::tc_fence_after();
+                issue_pv(st, big_slot);
+                ptx::tc_commit(&kv_empty[s]);   // every MMA reading this smem stage has been issued
+                if (has_next) {
+                    ptx::mbar_wait(&slot_free[big_slot], ip);
                     ptx::tc_fence_after();
-                    const uint32_t a_p = tmem_base + (uint32_t)(slot * SLOT_COLS);
-                    const uint32_t d_o = a_p + O_COL;
-#pragma unroll
-                    for (int k = 0; k < LP / 16; ++k) {
-                        const uint64_t dv =
-                            make_mnmajor_sw128_desc(st + Q_BYTES + KV_BYTES + (uint32_t)(k * 16 * 128));
-                        mma_f16_ts(d_o, a_p + (uint32_t)(8 * k), dv, idesc_o, (uint32_t)(k != 0));
-                    }
-                    ptx::tc_commit(&o_full[slot]);
+                    issue_s(stn, big_slot, 1);
                 }
-                ptx::tc_commit(&kv_empty[s]);   // every MMA reading this smem stage has retired
             }
         }
-    } else if (warp >= 4) {
+    } else {
         // ================= soft-max / epilogue warpgroups =================
-        const int slot = (warp - 4) >> 2;                 // warpgroup index == TMEM slot
+        const int slot = (warp - 2) >> 2;                 // warpgroup index == TMEM slot
         const int quarter = warp & 3;                     // TMEM lane quarter of this warp
         const uint32_t t_slot = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * SLOT_COLS);
         constexpr float kLog2e = 1.4426950408889634f;
@@ -217,7 +274,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, __nv_bfloat16 *
             ptx::tc_fence_after();
             float inv_sum = 0.0f;
             if (warp_has_rows) {
-                // pass 1: row maximum over the 197 real keys (TMEM loads software-pipelined)
+                // pass 1: row maximum over the 197 real keys (TMEM loads software-pipelined,
+                // 3-input max: one instruction per two scores)
                 float m = -INFINITY;
                 uint32_t r[2][16];
                 tmem_ld_x16(t_slot, r[0]);
@@ -226,13 +284,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, __nv_bfloat16 *
                     ptx::tmem_ld_wait();
                     if (ch + 1 < LP / 16) tmem_ld_x16(t_slot + (uint32_t)((ch + 1) * 16), r[(ch + 1) & 1]);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (ch * 16 + j < L) m = fmaxf(m, __uint_as_float(r[ch & 1][j]));
+                    for (int j = 0; j < 8; ++j) {
+                        const int c0 = ch * 16 + 2 * j;
+                        if (c0 + 1 < L) m = max3(m, __uint_as_float(r[ch & 1][2 * j]), __uint_as_float(r[ch & 1][2 * j + 1]));
+                        else if (c0 < L) m = fmaxf(m, __uint_as_float(r[ch & 1][2 * j]));
+                    }
                 }
-                // pass 2: p = exp(s - m), row sum, P (bf16) written over S columns already consumed
-                // (P columns [8ch, 8ch+8) overlay S columns that chunks <= ch have read)
+                // pass 2: p = exp2(s*log2e - m*log2e) on packed pairs (FFMA2 / FADD2), row sum,
+                // P (bf16) written over S columns already consumed (P columns [8ch, 8ch+8) overlay
+                // S columns that chunks <= ch have read)
                 const float mb = m * kLog2e;
-                float sum = 0.0f;
+                const f32x2 kl2 = pack2(kLog2e, kLog2e), kmb = pack2(-mb, -mb);
+                f32x2 sum2 = pack2(0.0f, 0.0f);
                 tmem_ld_x16(t_slot, r[0]);
 #pragma unroll
                 for (int ch = 0; ch < LP / 16; ++ch) {
@@ -241,15 +304,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, __nv_bfloat16 *
                     uint32_t pk[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        float p0 = exp2f(fmaf(__uint_as_float(r[ch & 1][2 * j]), kLog2e, -mb));
-                        float p1 = exp2f(fmaf(__uint_as_float(r[ch & 1][2 * j + 1]), kLog2e, -mb));
-                        if (ch * 16 + 2 * j >= L) p0 = 0.0f;
-                        if (ch * 16 + 2 * j + 1 >= L) p1 = 0.0f;
-                        sum += p0 + p1;
+                        const int c0 = ch * 16 + 2 * j;
+                        if (c0 >= L) { pk[j] = 0u; continue; }
+                        float t0, t1;
+                        unpack2(fma2(pack2(__uint_as_float(r[ch & 1][2 * j]), __uint_as_float(r[ch & 1][2 * j + 1])), kl2, kmb), t0, t1);
+                        const float p0 = ex2_approx(t0);
+                        const float p1 = c0 + 1 < L ? ex2_approx(t1) : 0.0f;
+                        sum2 = add2(sum2, pack2(p0, p1));
                         pk[j] = pack_bf16(p0, p1);
                     }
                     tmem_st_x8(t_slot + (uint32_t)(ch * 8), pk);
                 }
+                float sum, sum_hi;
+                unpack2(sum2, sum, sum_hi);
+                sum += sum_hi;
                 tmem_st_wait();
                 inv_sum = 1.0f / sum;
             }
@@ -258,26 +326,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, __nv_bfloat16 *
 
             ptx::mbar_wait(&o_full[slot], ip);
             ptx::tc_fence_after();
+            uint32_t o0[32], o1[32];
             if (warp_has_rows) {
-                uint32_t o0[32], o1[32];
                 ptx::tmem_ld_32x32b_x32(t_slot + O_COL, o0);
                 ptx::tmem_ld_32x32b_x32(t_slot + O_COL + 32, o1);
                 ptx::tmem_ld_wait();
-                if (row < L) {
-                    uint4 *dst = reinterpret_cast<uint4 *>(out + (img * L + row) * (int64_t)kWidth + head * HD);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const uint32_t *src = q < 4 ? &o0[8 * q] : &o1[8 * (q - 4)];
-                        dst[q] = make_uint4(
-                            pack_bf16(__uint_as_float(src[0]) * inv_sum, __uint_as_float(src[1]) * inv_sum),
-                            pack_bf16(__uint_as_float(src[2]) * inv_sum, __uint_as_float(src[3]) * inv_sum),
-                            pack_bf16(__uint_as_float(src[4]) * inv_sum, __uint_as_float(src[5]) * inv_sum),
-                            pack_bf16(__uint_as_float(src[6]) * inv_sum, __uint_as_float(src[7]) * inv_sum));
-                    }
-                }
             }
+            // O is in registers: the slot can take the next item's S while we normalise and store
             ptx::tc_fence_before();
             ptx::mbar_arrive(&slot_free[slot]);
+            if (warp_has_rows && row < L) {
+                uint4 *dst = reinterpret_cast<uint4 *>(out + (img * L + row) * (int64_t)kWidth + head * HD);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint32_t *src = q < 4 ? &o0[8 * q] : &o1[8 * (q - 4)];
+                    dst[q] = make_uint4(
+                        pack_bf16(__uint_as_float(src[0]) * inv_sum, __uint_as_float(src[1]) * inv_sum),
+                        pack_bf16(__uint_as_float(src[2]) * inv_sum, __uint_as_float(src[3]) * inv_sum),
+                        pack_bf16(__uint_as_float(src[4]) * inv_sum, __uint_as_float(src[5]) * inv_sum),
+                        pack_bf16(__uint_as_float(src[6]) * inv_sum, __uint_as_float(src[7]) * inv_sum));
+                }
+            }
         }
     }
 

@@ -35,11 +35,15 @@ constexpr int ACC_STAGES = 2;
 constexpr int A_BYTES = BM * BK * 2;          // 16 KiB
 constexpr int B_BYTES = (BN / 2) * BK * 2;    // 16 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int THREADS = 192;
-constexpr int EPI_WARPS = 4;
 constexpr int SLAB_BYTES = 4096;              // 32 rows x 128 B, SWIZZLE_128B
-constexpr int SLABS_PER_WARP = 4;             // bf16: 2 out; f32: 2 in + 2 out
-constexpr int EPI_BYTES = EPI_WARPS * SLABS_PER_WARP * SLAB_BYTES;   // 64 KiB
+constexpr int EPI_BYTES = 64 * 1024;          // bf16: 8 warps x 2 out slabs; f32: 4 warps x (2 in + 2 out)
+// bf16 epilogues (bias, QuickGELU) are instruction-bound: 8 warps, two per TMEM lane quarter, each
+// owning half of the 256 columns.  The fp32 residual epilogue is memory-bound: 4 warps.
+template <int EPI> struct EpiCfg {
+    static constexpr int kWarps = EPI == VG_EPI_BIAS_RESID_F32 ? 4 : 8;
+    static constexpr int kSlabs = EPI == VG_EPI_BIAS_RESID_F32 ? 4 : 2;
+    static constexpr int kThreads = 64 + 32 * kWarps;
+};
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 512;
 
 struct Params {
@@ -50,7 +54,11 @@ struct Params {
 
 __device__ __forceinline__ float quick_gelu(float v)
 {
-    return __fdividef(v, 1.0f + __expf(-1.702f * v));
+    // x * sigmoid(1.702 x) with sigmoid(z) = 0.5 * tanh(z / 2) + 0.5: one MUFU op per element
+    // (tanh.approx, relative error ~2^-11, below the bf16 rounding of the output)
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * v));
+    return v * fmaf(0.5f, t, 0.5f);
 }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
 {
@@ -61,7 +69,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
 __device__ __forceinline__ uint32_t slab_off(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
 
 template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<EPI>::kThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
              const __grid_constant__ CUtensorMap tma_out, const Params p)
 {
@@ -74,8 +82,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     uint64_t *empty_bar = bars + STAGES;                     // [STAGES]   (per CTA)
     uint64_t *tmem_full = bars + 2 * STAGES;                 // [ACC]      (per CTA)
     uint64_t *tmem_empty = bars + 2 * STAGES + ACC_STAGES;   // [ACC]      (leader's are used)
-    uint64_t *xin_bar = bars + 2 * STAGES + 2 * ACC_STAGES;  // [EPI_WARPS][2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(xin_bar + 2 * EPI_WARPS);
+    constexpr int EPI_WARPS = EpiCfg<EPI>::kWarps;
+    constexpr int SLABS_PER_WARP = EpiCfg<EPI>::kSlabs;
+    uint64_t *xin_bar = bars + 2 * STAGES + 2 * ACC_STAGES;  // [4][2] (fp32 residual path)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(xin_bar + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();
@@ -98,7 +108,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             ptx::mbar_init(&tmem_full[s], 1);
             ptx::mbar_init(&tmem_empty[s], 2 * EPI_WARPS);   // one arrival per epilogue warp, both CTAs
         }
-        for (int s = 0; s < 2 * EPI_WARPS; ++s) ptx::mbar_init(&xin_bar[s], 1);
+        for (int s = 0; s < 8; ++s) ptx::mbar_init(&xin_bar[s], 1);
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -160,8 +170,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     } else {
         // ================= epilogue warps (both CTAs) =================
         const int ew = warp & 3;                  // TMEM lane quarter this warp may touch
+        const int chalf = (warp - 2) >> 2;        // column half (8-warp epilogues), else 0
         const int lane_base = ew * 32;
-        unsigned char *slab = epi_smem + (size_t)ew * SLABS_PER_WARP * SLAB_BYTES;
+        unsigned char *slab = epi_smem + (size_t)(warp - 2) * SLABS_PER_WARP * SLAB_BYTES;
         uint64_t *xbar = xin_bar + 2 * ew;
         uint32_t xphase[2] = {0u, 0u};
         int as = 0;
@@ -223,11 +234,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                     obuf ^= 1;
                 }
             } else {
-                // bf16 output: 4 chunks of 64 columns, slabs 0,1 = out (2 x [32 rows x 64 bf16])
+                // bf16 output: this warp's half of the tile in 2 chunks of 64 columns,
+                // slabs 0,1 = out (2 x [32 rows x 64 bf16])
                 ptx::mbar_wait(&tmem_full[as], aphase);
                 ptx::tc_fence_after();
 #pragma unroll 1
-                for (int ch = 0; ch < BN / 64; ++ch) {
+                for (int ch = 2 * chalf; ch < 2 * chalf + 2; ++ch) {
                     uint32_t r0[32], r1[32];
                     ptx::tmem_ld_32x32b_x32(tbase + (uint32_t)(ch * 64), r0);
                     ptx::tmem_ld_32x32b_x32(tbase + (uint32_t)(ch * 64 + 32), r1);
@@ -334,7 +346,7 @@ int launch_t(VgHandle *h, const GemmArgs &g, cudaStream_t st)
                      : EPI == VG_EPI_BIAS_QGELU_BF16 ? VG_K_GEMM_FC
                      : (g.K == kMlp ? VG_K_GEMM_PROJ : VG_K_GEMM_OUT);
     VgProfScope prof(h, kind, 2.0 * (double)g.M * g.N * (double)g.K, st);
-    gemm2_kernel<EPI><<<2 * clusters, THREADS, SMEM_BYTES, st>>>(ta, tb, to, p);
+    gemm2_kernel<EPI><<<2 * clusters, EpiCfg<EPI>::kThreads, SMEM_BYTES, st>>>(ta, tb, to, p);
     VG_LAUNCH_CHECK(h);
     return VG_OK;
 }
