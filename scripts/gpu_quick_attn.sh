@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 120 python -m pytest tests/test_vit_gpu.py -q -m gpu -k "attention" -x 2>&1 | tail -1
+ONLY=attention timeout 200 python scripts/bench_kernels.py

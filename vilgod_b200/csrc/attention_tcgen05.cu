@@ -14,6 +14,7 @@
 // row) and small (69 row) query blocks alternate between the two warpgroups from item to item.
 // The 1/sqrt(64) query scale is folded into the in-proj weights (vit_misc.cu).
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -134,8 +135,11 @@ __host__ __device__ constexpr uint32_t idesc_bf16(uint32_t M, uint32_t N, uint32
 
 __global__ void __launch_bounds__(THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, __nv_bfloat16 *__restrict__ out,
-                    int64_t num_items)
+                    int64_t num_items, long long *trace)
 {
+    // optional timeline trace (test hook): CTA 0 records clock64 stamps of its first 8 items
+#define VG_TRACE(evt, it_) do { if (trace && blockIdx.x == 0 && (it_) < 8) trace[(evt) * 8 + (it_)] = clock64(); } while (0)
+
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -191,9 +195,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, __nv_bfloat16 *
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        // Software-pipelined so that each warpgroup's next S is queued as early as its TMEM slot
-        // allows: ... PV(small, i) -> S(big, i+1) -> PV(big, i) -> S(small, i+1) -> PV(small, i+1) ...
-        // (the slot that held the small block of item i takes the big block of item i+1)
+        // Event driven: each TMEM slot alternates between "P ready -> issue O = P V" and
+        // "slot drained and next Q/K/V landed -> issue S = Q K^T of the next item".  Whichever slot is
+        // ready first is served first (non-blocking mbarrier probes), so a warpgroup never waits
+        // behind the other one's hand-off.
         if (lane == 0) {
             constexpr uint32_t idesc_s = idesc_bf16(128, LP, 0);   // S = Q K^T, both K-major
             constexpr uint32_t idesc_o = idesc_bf16(128, HD, 1);   // O = P V, V is MN-major
@@ -218,41 +223,46 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, __nv_bfloat16 *
                 }
                 ptx::tc_commit(&o_full[slot]);
             };
-            int it = 0;
-            if ((int64_t)blockIdx.x < num_items) {      // prologue: both S of the first item
-                const uint32_t st0 = ptx::smem_u32(smem);
-                ptx::mbar_wait(&kv_full[0], 0u);
-                ptx::tc_fence_after();
-                issue_s(st0, 0, 0);
-                issue_s(st0, 1, 1);
-            }
-            for (int64_t item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-                const int s = it & 1;
-                const uint32_t ip = (uint32_t)it & 1u;
-                const uint32_t st = ptx::smem_u32(smem + (size_t)s * STAGE_BYTES);
-                const int small_slot = 1 ^ (int)ip, big_slot = (int)ip;
-                const bool has_next = item + gridDim.x < num_items;
-                const int sn = (it + 1) & 1;
-                const uint32_t phn = (uint32_t)((it + 1) >> 1) & 1u;
-                const uint32_t stn = ptx::smem_u32(smem + (size_t)sn * STAGE_BYTES);
-
-                ptx::mbar_wait(&p_full[small_slot], ip);
-                ptx::tc_fence_after();
-                issue_pv(st, small_slot);
-                if (has_next) {
-                    ptx::mbar_wait(&kv_full[sn], phn);
-                    ptx::mbar_wait(&slot_free[small_slot], ip);   // its O of this item has been read
-                    ptx::tc_fence_after();
-                    issue_s(stn, small_slot, 0);
-                }
-                ptx::mbar_wait(&p_full[big_slot], ip);
-                ptx::tc_fence_after();
-                issue_pv(st, big_slot);
-                ptx::tc_commit(&kv_empty[s]);   // every MMA reading this smem stage has been issued
-                if (has_next) {
-                    ptx::mbar_wait(&slot_free[big_slot], ip);
-                    ptx::tc_fence_after();
-                    issue_s(stn, big_slot, 1);
+            const int n_my = (int)((num_items - blockIdx.x + gridDim.x - 1) / gridDim.x);   // >= 1
+            int it_s[2] = {0, 0};       // next item whose S this slot issues
+            int it_pv[2] = {0, 0};      // next item whose PV this slot issues
+            int pv_done0 = 0, pv_done1 = 0;   // PVs issued per smem stage, to release the stage
+            int kv_seen = -1;           // highest item whose Q/K/V are known to have landed
+            while (it_pv[0] < n_my || it_pv[1] < n_my) {
+#pragma unroll
+                for (int slot = 0; slot < 2; ++slot) {
+                    // ---- S of item it_s[slot] into this slot ----
+                    if (it_s[slot] < n_my && it_s[slot] == it_pv[slot]) {
+                        const int it = it_s[slot];
+                        bool ok = true;
+                        if (it > 0) ok = ptx::mbar_test(&slot_free[slot], (uint32_t)(it - 1) & 1u);
+                        if (ok && kv_seen < it) {
+                            ok = ptx::mbar_test(&kv_full[it & 1], (uint32_t)(it >> 1) & 1u);
+                            if (ok) kv_seen = it;
+                        }
+                        if (ok) {
+                            ptx::tc_fence_after();
+                            VG_TRACE(10 + slot, it);
+                            issue_s(ptx::smem_u32(smem + (size_t)(it & 1) * STAGE_BYTES), slot,
+                                    slot ^ (it & 1));
+                            it_s[slot] = it + 1;
+                        }
+                    }
+                    // ---- O = P V of item it_pv[slot] ----
+                    if (it_pv[slot] < it_s[slot]) {
+                        const int it = it_pv[slot];
+                        if (ptx::mbar_test(&p_full[slot], (uint32_t)it & 1u)) {
+                            ptx::tc_fence_after();
+                            VG_TRACE(12 + slot, it);
+                            issue_pv(ptx::smem_u32(smem + (size_t)(it & 1) * STAGE_BYTES), slot);
+                            it_pv[slot] = it + 1;
+                            int &cnt = (it & 1) ? pv_done1 : pv_done0;
+                            if (++cnt == 2) {                  // both slots are done with this stage
+                                cnt = 0;
+                                ptx::tc_commit(&kv_empty[it & 1]);
+                            }
+                        }
+                    }
                 }
             }
         }
@@ -271,6 +281,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, __nv_bfloat16 *
             const int row = blk * 128 + quarter * 32 + lane;
             const bool warp_has_rows = blk * 128 + quarter * 32 < L;      // warp-uniform
             ptx::mbar_wait(&s_full[slot], ip);
+            if (quarter == 0 && lane == 0) VG_TRACE(slot * 5 + 0, it);
             ptx::tc_fence_after();
             float inv_sum = 0.0f;
             if (warp_has_rows) {
@@ -294,6 +305,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, __nv_bfloat16 *
                 // P (bf16) written over S columns already consumed (P columns [8ch, 8ch+8) overlay
                 // S columns that chunks <= ch have read)
                 const float mb = m * kLog2e;
+                if (quarter == 0 && lane == 0) VG_TRACE(slot * 5 + 1, it);
                 const f32x2 kl2 = pack2(kLog2e, kLog2e), kmb = pack2(-mb, -mb);
                 f32x2 sum2 = pack2(0.0f, 0.0f);
                 tmem_ld_x16(t_slot, r[0]);
@@ -322,9 +334,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, __nv_bfloat16 *
                 inv_sum = 1.0f / sum;
             }
             ptx::tc_fence_before();
-            ptx::mbar_arrive(&p_full[slot]);
+            if (quarter == 0 && lane == 0) VG_TRACE(slot * 5 + 2, it);
+            ptx::mbar_arrive_relaxed(&p_full[slot]);
 
             ptx::mbar_wait(&o_full[slot], ip);
+            if (quarter == 0 && lane == 0) VG_TRACE(slot * 5 + 3, it);
             ptx::tc_fence_after();
             uint32_t o0[32], o1[32];
             if (warp_has_rows) {
@@ -334,7 +348,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, __nv_bfloat16 *
             }
             // O is in registers: the slot can take the next item's S while we normalise and store
             ptx::tc_fence_before();
-            ptx::mbar_arrive(&slot_free[slot]);
+            if (quarter == 0 && lane == 0) VG_TRACE(slot * 5 + 4, it);
+            ptx::mbar_arrive_relaxed(&slot_free[slot]);
             if (warp_has_rows && row < L) {
                 uint4 *dst = reinterpret_cast<uint4 *>(out + (img * L + row) * (int64_t)kWidth + head * HD);
 #pragma unroll
@@ -392,7 +407,20 @@ int launch_attention_tc(VgHandle *h, const __nv_bfloat16 *qkv, int64_t B, __nv_b
     const int64_t items = B * kHeads;
     const int grid = (int)(items < h->num_sms ? items : h->num_sms);
     VgProfScope prof(h, VG_K_ATTENTION, 4.0 * (double)B * kHeads * L * L * HD, st);
-    attention_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(map, out, items);
+    static long long *trace = nullptr;
+    if (!trace && getenv("VG_ATTN_TRACE")) cudaMalloc(&trace, 16 * 8 * sizeof(long long));
+    attention_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(map, out, items, trace);
+    if (trace) {
+        long long hbuf[16 * 8];
+        cudaMemcpy(hbuf, trace, sizeof(hbuf), cudaMemcpyDeviceToHost);
+        const char *names[14] = {"wg0 S ready", "wg0 max done", "wg0 P done", "wg0 O ready", "wg0 slot free", "wg1 S ready", "wg1 max done", "wg1 P done", "wg1 O ready", "wg1 slot free", "mma S slot0", "mma S slot1", "mma PV slot0", "mma PV slot1"};
+        long long t0 = hbuf[10 * 8];
+        for (int e = 0; e < 14; ++e) {
+            printf("%-14s", names[e]);
+            for (int i = 0; i < 8; ++i) printf(" %8lld", hbuf[e * 8 + i] - t0);
+            printf("\n");
+        }
+    }
     VG_LAUNCH_CHECK(h);
     return VG_OK;
 }

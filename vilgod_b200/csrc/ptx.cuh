@@ -49,6 +49,26 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// arrive without release ordering of the thread's earlier generic-proxy memory operations: for
+// hand-offs whose payload lives in tensor memory (ordered by tcgen05.fence::before_thread_sync), so
+// the arrival does not have to wait for outstanding global stores to drain
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// non-blocking probe: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     asm volatile(
