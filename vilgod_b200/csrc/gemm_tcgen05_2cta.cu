@@ -142,28 +142,36 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ================= MMA issuer (leader CTA, one lane) =================
-        if (leader && lane == 0) {
+        // The leader's whole warp runs the loop convergently; one elected lane issues the tcgen05
+        // instructions.  With a lone divergent lane ptxas wraps every UTCHMMA in an ELECT / R2UR
+        // waterfall; convergent code keeps descriptors and TMEM addresses in uniform registers.
+        if (leader) {
             constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(2 * BM, BN);
+            const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
             int stage = 0, as = 0;
             uint32_t phase = 0, aphase = 0;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 ptx::mbar_wait(&tmem_empty[as], aphase ^ 1u);
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+                const uint32_t d_tmem = tb + (uint32_t)(as * BN);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
                     const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * STAGE_BYTES);
                     const uint64_t da = ptx::make_kmajor_sw128_desc(sa);
                     const uint64_t db = ptx::make_kmajor_sw128_desc(sa + A_BYTES);
+                    if (ptx::elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / UK; ++k)
-                        ptx::mma_f16_ss_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k),
-                                             idesc, (uint32_t)((kb | k) != 0));
-                    ptx::tc_commit_pair(&empty_bar[stage], 3);   // stage free in both CTAs
+                        for (int k = 0; k < BK / UK; ++k)
+                            ptx::mma_f16_ss_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k),
+                                                 idesc, (uint32_t)((kb | k) != 0));
+                        ptx::tc_commit_pair(&empty_bar[stage], 3);   // stage free in both CTAs
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
-                ptx::tc_commit_pair(&tmem_full[as], 3);          // accumulator ready in both CTAs
+                if (ptx::elect_one()) ptx::tc_commit_pair(&tmem_full[as], 3);   // accumulator ready
+                __syncwarp();
                 if (++as == ACC_STAGES) { as = 0; aphase ^= 1u; }
             }
         }
