@@ -1,5 +1,7 @@
 // C ABI of libvilgod_b200.so (see include/vilgod_b200.h for the contract and the reference
 // interfaces each entry point replaces).
+#include <stdlib.h>
+
 #include <new>
 
 #include "common.cuh"
@@ -17,9 +19,11 @@ constexpr size_t kTileBytesPerImage = (size_t)VG_TILE_ELEMS * 2;
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct EncodeBuffers {
-    float *x;
-    __nv_bfloat16 *y;
-    __nv_bfloat16 *big;
+    float *x;               // residual stream fp32 [M,768]
+    __nv_bfloat16 *y;       // attention output (A of out-proj) [M,768]; LayerNorm output when unfused
+    __nv_bfloat16 *big;     // qkv [M,2304] / MLP hidden [M,3072]
+    __nv_bfloat16 *xb;      // bf16 copy of the residual stream (A of the LayerNorm-folded GEMMs)
+    float *stats;           // row sum / sum of squares of the residual stream [M,3,2]
 };
 
 EncodeBuffers carve(void *ws, int64_t chunk)
@@ -31,6 +35,10 @@ EncodeBuffers carve(void *ws, int64_t chunk)
     b.y = reinterpret_cast<__nv_bfloat16 *>(p);
     p += align_up((size_t)chunk * kTokens * kWidth * 2, 1024);
     b.big = reinterpret_cast<__nv_bfloat16 *>(p);
+    p += align_up((size_t)chunk * kTokens * kMlp * 2, 1024);
+    b.xb = reinterpret_cast<__nv_bfloat16 *>(p);
+    p += align_up((size_t)chunk * kTokens * kWidth * 2, 1024);
+    b.stats = reinterpret_cast<float *>(p);
     return b;
 }
 
@@ -38,7 +46,9 @@ size_t encode_bytes(int64_t chunk)
 {
     return align_up((size_t)chunk * kTokens * kWidth * 4, 1024) +
            align_up((size_t)chunk * kTokens * kWidth * 2, 1024) +
-           align_up((size_t)chunk * kTokens * kMlp * 2, 1024);
+           align_up((size_t)chunk * kTokens * kMlp * 2, 1024) +
+           align_up((size_t)chunk * kTokens * kWidth * 2, 1024) +
+           align_up((size_t)chunk * kTokens * 6 * 4, 1024);
 }
 
 // the visual tower on `n` images whose patch-major tiles start at `tiles`
@@ -53,21 +63,47 @@ int encode_chunk(VgHandle *h, const __nv_bfloat16 *tiles, int64_t n, const Encod
     // patch embedding: [n*196, 256] x [768, 256]^T  (+ b_eff + positional embedding)
     g = GemmArgs{tiles, w.w_patch, w.patch_bias_pos, eb.x, n * kPatches, kWidth, kPatchK, kEpiPatch};
     if ((rc = launch_gemm(h, g, st))) return rc;
-    if ((rc = launch_ln_pre(h, eb.x, n, st))) return rc;
+    // LayerNorm is folded into the GEMMs (no LayerNorm kernel, no normalised copy in HBM):
+    // residual-producing epilogues emit a bf16 copy of x plus per-row sum / sum of squares, the
+    // QKV and c_fc GEMMs multiply the raw bf16 residual by gamma-scaled weights and normalise in
+    // their epilogue.  VG_LN_UNFUSED=1 selects the separate LayerNorm kernels (A/B, debugging).
+    static const bool unfused = getenv("VG_LN_UNFUSED") != nullptr;
+    if ((rc = launch_ln_pre(h, eb.x, n, unfused ? nullptr : eb.xb, unfused ? nullptr : eb.stats, st)))
+        return rc;
     const int stop = dbg ? dbg->stop_after_layer : -1;
     bool stopped = stop == -2;
     for (int l = 0; l < kLayers && !stopped; ++l) {
         const LayerDev &L = w.layer[l];
-        if ((rc = launch_layernorm_bf16(h, eb.x, L.ln1_w, L.ln1_b, M, eb.y, st))) return rc;
-        g = GemmArgs{eb.y, L.w_qkv, L.b_qkv, eb.big, M, 3 * kWidth, kWidth, VG_EPI_BIAS_BF16};
+        if (unfused) {
+            if ((rc = launch_layernorm_bf16(h, eb.x, L.ln1_w, L.ln1_b, M, eb.y, st))) return rc;
+            g = GemmArgs{eb.y, L.w_qkv, L.b_qkv, eb.big, M, 3 * kWidth, kWidth, VG_EPI_BIAS_BF16};
+        } else {
+            g = GemmArgs{eb.xb, L.wf_qkv, L.c_qkv, eb.big, M, 3 * kWidth, kWidth, VG_EPI_BIAS_BF16};
+            g.stats = eb.stats;
+            g.colsum = L.s_qkv;
+        }
         if ((rc = launch_gemm(h, g, st))) return rc;
         if ((rc = launch_attention(h, eb.big, n, eb.y, st))) return rc;
         g = GemmArgs{eb.y, L.w_out, L.b_out, eb.x, M, kWidth, kWidth, VG_EPI_BIAS_RESID_F32};
+        if (!unfused) {
+            g.stats = eb.stats;
+            g.xb_out = eb.xb;
+        }
         if ((rc = launch_gemm(h, g, st))) return rc;
-        if ((rc = launch_layernorm_bf16(h, eb.x, L.ln2_w, L.ln2_b, M, eb.y, st))) return rc;
-        g = GemmArgs{eb.y, L.w_fc, L.b_fc, eb.big, M, kMlp, kWidth, VG_EPI_BIAS_QGELU_BF16};
+        if (unfused) {
+            if ((rc = launch_layernorm_bf16(h, eb.x, L.ln2_w, L.ln2_b, M, eb.y, st))) return rc;
+            g = GemmArgs{eb.y, L.w_fc, L.b_fc, eb.big, M, kMlp, kWidth, VG_EPI_BIAS_QGELU_BF16};
+        } else {
+            g = GemmArgs{eb.xb, L.wf_fc, L.c_fc, eb.big, M, kMlp, kWidth, VG_EPI_BIAS_QGELU_BF16};
+            g.stats = eb.stats;
+            g.colsum = L.s_fc;
+        }
         if ((rc = launch_gemm(h, g, st))) return rc;
         g = GemmArgs{eb.big, L.w_proj, L.b_proj, eb.x, M, kWidth, kMlp, VG_EPI_BIAS_RESID_F32};
+        if (!unfused && l + 1 < kLayers && stop != l) {   // the next layer's ln_1 needs xb / stats
+            g.stats = eb.stats;
+            g.xb_out = eb.xb;
+        }
         if ((rc = launch_gemm(h, g, st))) return rc;
         if (stop == l) stopped = true;
     }

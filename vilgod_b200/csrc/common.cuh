@@ -28,6 +28,10 @@ constexpr int kMaxPrompts = 64;
 struct LayerDev {
     __nv_bfloat16 *w_qkv, *w_out, *w_fc, *w_proj;   // [N,K] row-major bf16
     float *b_qkv, *b_out, *b_fc, *b_proj;           // fp32
+    // LayerNorm-folded variants of the two GEMMs that consume a LayerNorm output:
+    //   W' = W o gamma (bf16), colsum_n = sum_k W'[n][k], c_n = sum_k beta_k W[n][k] + b_n
+    __nv_bfloat16 *wf_qkv, *wf_fc;
+    float *s_qkv, *c_qkv, *s_fc, *c_fc;
     float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
 };
 
@@ -132,6 +136,10 @@ struct GemmArgs {
     int64_t M;
     int32_t N, K;
     int32_t epilogue;         // VG_EPI_* or kEpiPatch
+    // LayerNorm folding (2-CTA kernel only; all null = plain epilogues)
+    float *stats = nullptr;            // [M][3][2] per column tile: row sum / sum of squares
+    const float *colsum = nullptr;     // [N] sum_k W'[n][k]   (bf16 epilogues consuming `stats`)
+    __nv_bfloat16 *xb_out = nullptr;   // [M][768] bf16 copy of the new residual (residual epilogue)
 };
 constexpr int kEpiPatch = 3;  // out fp32 x[img*197 + 1 + p][n] = acc + table[1+p][n]
 int launch_gemm(VgHandle *h, const GemmArgs &g, cudaStream_t st);
@@ -144,7 +152,7 @@ int launch_attention_tc(VgHandle *h, const __nv_bfloat16 *qkv, int64_t B, __nv_b
 int launch_layernorm_bf16(VgHandle *h, const float *x, const float *w, const float *b,
                           int64_t rows, __nv_bfloat16 *y, cudaStream_t st);
 // x[img,0,:] = table[0]; then x = LN(x) in place (ln_pre) over all B*197 rows
-int launch_ln_pre(VgHandle *h, float *x, int64_t B, cudaStream_t st);
+int launch_ln_pre(VgHandle *h, float *x, int64_t B, __nv_bfloat16 *xb, float *stats, cudaStream_t st);
 // ln_post on CLS rows -> proj -> L2 norm -> logits -> softmax -> argmax
 int launch_head(VgHandle *h, const float *x, int64_t B, float *probs, int32_t *top1, float *feats,
                 float *logits, cudaStream_t st);

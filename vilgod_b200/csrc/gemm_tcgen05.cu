@@ -305,6 +305,10 @@ int launch_gemm(VgHandle *h, const GemmArgs &g, cudaStream_t st)
     // kernel below serves the patch embedding (row-remapping epilogue) and VG_GEMM_V1=1 (A/B runs).
     static const bool force_v1 = getenv("VG_GEMM_V1") != nullptr;
     if (g.epilogue != kEpiPatch && !force_v1) return launch_gemm_2cta(h, g, st);
+    if (g.stats) {
+        VG_SET_ERR(h, "VG_GEMM_V1 has no LayerNorm-folded epilogues: set VG_LN_UNFUSED=1 as well");
+        return VG_EINVAL;
+    }
     switch (g.epilogue) {
         case VG_EPI_BIAS_BF16: return launch_gemm_t<VG_EPI_BIAS_BF16>(h, g, st);
         case VG_EPI_BIAS_QGELU_BF16: return launch_gemm_t<VG_EPI_BIAS_QGELU_BF16>(h, g, st);

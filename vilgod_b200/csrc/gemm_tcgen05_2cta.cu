@@ -30,24 +30,33 @@ namespace {
 constexpr int BM = 128;            // rows per CTA (256 per pair)
 constexpr int BN = 256;            // UMMA N; each CTA stages BN/2 rows of W
 constexpr int BK = 64, UK = 16;
-constexpr int STAGES = 4;
 constexpr int ACC_STAGES = 2;
 constexpr int A_BYTES = BM * BK * 2;          // 16 KiB
 constexpr int B_BYTES = (BN / 2) * BK * 2;    // 16 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int SLAB_BYTES = 4096;              // 32 rows x 128 B, SWIZZLE_128B
-constexpr int EPI_BYTES = 64 * 1024;          // bf16: 8 warps x 2 out slabs; f32: 4 warps x (2 in + 2 out)
 // bf16 epilogues (bias, QuickGELU) are instruction-bound: 8 warps, two per TMEM lane quarter, each
 // owning half of the 256 columns.  The fp32 residual epilogue is memory-bound: 4 warps.
-template <int EPI> struct EpiCfg {
-    static constexpr int kWarps = EPI == VG_EPI_BIAS_RESID_F32 ? 4 : 8;
-    static constexpr int kSlabs = EPI == VG_EPI_BIAS_RESID_F32 ? 4 : 2;
+// LNF ("LayerNorm folded"):
+//   residual epilogue  : additionally emits a bf16 copy of the new residual stream (the next
+//                        GEMM's A operand) and accumulates per-row sum / sum-of-squares
+//   bf16 epilogues     : A is the RAW residual stream in bf16, W carries the LayerNorm gain, and the
+//                        normalisation is applied after the matmul:
+//                        y = rstd_i * (acc - mu_i * colsum_n) + c_n      (model.py:157-163,190-191)
+template <int EPI, bool LNF> struct EpiCfg {
+    static constexpr bool kResid = EPI == VG_EPI_BIAS_RESID_F32;
+    static constexpr int kWarps = kResid ? 4 : 8;
+    static constexpr int kSlabs = kResid ? (LNF ? 6 : 4) : 2;   // f32: 2 in + 2 out (+ 2 bf16 out)
     static constexpr int kThreads = 64 + 32 * kWarps;
+    static constexpr int kStages = 4;
+    static constexpr int kEpiBytes = kWarps * kSlabs * SLAB_BYTES;          // 64 KiB / 96 KiB
+    static constexpr size_t kSmem = (size_t)kStages * STAGE_BYTES + kEpiBytes + 1024 + 512;
 };
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 512;
 
 struct Params {
-    const float *bias;
+    const float *bias;       // [N]: bias, or c_n for LN-folded epilogues
+    const float *colsum;     // [N]: sum_k W'[n][k] (LN-folded bf16 epilogues)
+    float *stats;            // [M][3][2] per 256-column tile: row sum / sum of squares of the residual
     int64_t M;
     int32_t N, K;
 };
@@ -68,11 +77,14 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
 // 16-byte chunk c of row r inside a 1024-byte-aligned SWIZZLE_128B slab
 __device__ __forceinline__ uint32_t slab_off(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
 
-template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<EPI>::kThreads, 1)
+template <int EPI, bool LNF>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<EPI, LNF>::kThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-             const __grid_constant__ CUtensorMap tma_out, const Params p)
+             const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_xb,
+             const Params p)
 {
+    constexpr int STAGES = EpiCfg<EPI, LNF>::kStages;
+    constexpr int EPI_BYTES = EpiCfg<EPI, LNF>::kEpiBytes;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -82,8 +94,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     uint64_t *empty_bar = bars + STAGES;                     // [STAGES]   (per CTA)
     uint64_t *tmem_full = bars + 2 * STAGES;                 // [ACC]      (per CTA)
     uint64_t *tmem_empty = bars + 2 * STAGES + ACC_STAGES;   // [ACC]      (leader's are used)
-    constexpr int EPI_WARPS = EpiCfg<EPI>::kWarps;
-    constexpr int SLABS_PER_WARP = EpiCfg<EPI>::kSlabs;
+    constexpr int EPI_WARPS = EpiCfg<EPI, LNF>::kWarps;
+    constexpr int SLABS_PER_WARP = EpiCfg<EPI, LNF>::kSlabs;
     uint64_t *xin_bar = bars + 2 * STAGES + 2 * ACC_STAGES;  // [4][2] (fp32 residual path)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(xin_bar + 8);
 
@@ -100,6 +112,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         ptx::prefetch_tensormap(&tma_a);
         ptx::prefetch_tensormap(&tma_b);
         ptx::prefetch_tensormap(&tma_out);
+        if (EPI == VG_EPI_BIAS_RESID_F32 && LNF) ptx::prefetch_tensormap(&tma_xb);
         for (int s = 0; s < STAGES; ++s) {
             ptx::mbar_init(&full_bar[s], 1);
             ptx::mbar_init(&empty_bar[s], 1);
@@ -201,6 +214,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                 }
                 ptx::mbar_wait(&tmem_full[as], aphase);
                 ptx::tc_fence_after();
+                float rs = 0.0f, rq = 0.0f;      // row sum / sum of squares of the new residual (LNF)
 #pragma unroll 1
                 for (int ch = 0; ch < BN / 32; ++ch) {
                     const int ib = ch & 1;
@@ -232,18 +246,49 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                         o.z = x.z + (__uint_as_float(r[4 * q + 2]) + bv.z);
                         o.w = x.w + (__uint_as_float(r[4 * q + 3]) + bv.w);
                         *reinterpret_cast<float4 *>(xout + off) = o;
+                        if (LNF) {
+                            rs += (o.x + o.y) + (o.z + o.w);
+                            rq += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+                            // bf16 copy: two 32-column chunks share one 64-column slab row (128 B)
+                            unsigned char *xb = slab + (4 + ((ch >> 1) & 1)) * SLAB_BYTES;
+                            uint2 pk = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+                            *reinterpret_cast<uint2 *>(xb + slab_off(lane, (ch & 1) * 4 + (q >> 1)) +
+                                                       (q & 1) * 8) = pk;
+                        }
                     }
                     ptx::fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
                         ptx::tma_store_2d(&tma_out, xout, col0 + ch * 32, row0);
+                        if (LNF && (ch & 1))   // same bulk group as this chunk's fp32 store
+                            ptx::tma_store_2d(&tma_xb, slab + (4 + ((ch >> 1) & 1)) * SLAB_BYTES,
+                                              col0 + (ch - 1) * 32, row0);
                         ptx::tma_store_commit();
                     }
                     obuf ^= 1;
                 }
+                if (LNF) {
+                    const int64_t row = (int64_t)row0 + lane;
+                    // one slot per 256-column tile, summed in fixed order by the consumer:
+                    // deterministic (no atomics) and nothing to clear between GEMMs
+                    if (row < p.M)
+                        *reinterpret_cast<float2 *>(p.stats + 6 * row + 2 * n_blk) = make_float2(rs, rq);
+                }
             } else {
                 // bf16 output: this warp's half of the tile in 2 chunks of 64 columns,
                 // slabs 0,1 = out (2 x [32 rows x 64 bf16])
+                float mu = 0.0f, rstd = 1.0f;
+                if (LNF) {
+                    const int64_t row = (int64_t)row0 + lane;
+                    if (row < p.M) {
+                        const float2 *sp = reinterpret_cast<const float2 *>(p.stats + 6 * row);
+                        const float2 s0 = sp[0], s1 = sp[1], s2 = sp[2];
+                        mu = ((s0.x + s1.x) + s2.x) * (1.0f / kWidth);
+                        const float var = fmaxf(((s0.y + s1.y) + s2.y) * (1.0f / kWidth) - mu * mu, 0.0f);
+                        rstd = rsqrtf(var + 1e-5f);
+                    }
+                }
+                const float nmu = -mu;
                 ptx::mbar_wait(&tmem_full[as], aphase);
                 ptx::tc_fence_after();
 #pragma unroll 1
@@ -256,14 +301,25 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                     ptx::tmem_ld_wait();
                     unsigned char *out = slab + obuf * SLAB_BYTES;
                     const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + col0 + ch * 64);
+                    const float4 *s4 = reinterpret_cast<const float4 *>(p.colsum + col0 + ch * 64);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const uint32_t *src = q < 4 ? &r0[8 * q] : &r1[8 * (q - 4)];
                         const float4 ba = __ldg(b4 + 2 * q), bb = __ldg(b4 + 2 * q + 1);
-                        float v[8] = {__uint_as_float(src[0]) + ba.x, __uint_as_float(src[1]) + ba.y,
-                                      __uint_as_float(src[2]) + ba.z, __uint_as_float(src[3]) + ba.w,
-                                      __uint_as_float(src[4]) + bb.x, __uint_as_float(src[5]) + bb.y,
-                                      __uint_as_float(src[6]) + bb.z, __uint_as_float(src[7]) + bb.w};
+                        float v[8];
+                        if (LNF) {
+                            const float4 sa = __ldg(s4 + 2 * q), sb = __ldg(s4 + 2 * q + 1);
+                            const float sv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+                            const float cv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                v[j] = fmaf(rstd, fmaf(nmu, sv[j], __uint_as_float(src[j])), cv[j]);
+                        } else {
+                            v[0] = __uint_as_float(src[0]) + ba.x; v[1] = __uint_as_float(src[1]) + ba.y;
+                            v[2] = __uint_as_float(src[2]) + ba.z; v[3] = __uint_as_float(src[3]) + ba.w;
+                            v[4] = __uint_as_float(src[4]) + bb.x; v[5] = __uint_as_float(src[5]) + bb.y;
+                            v[6] = __uint_as_float(src[6]) + bb.z; v[7] = __uint_as_float(src[7]) + bb.w;
+                        }
                         if (EPI == VG_EPI_BIAS_QGELU_BF16) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) v[j] = quick_gelu(v[j]);
@@ -322,10 +378,10 @@ int make_tmap(VgHandle *h, CUtensorMap *map, CUtensorMapDataType dt, int elt_byt
     return VG_OK;
 }
 
-template <int EPI>
+template <int EPI, bool LNF>
 int launch_t(VgHandle *h, const GemmArgs &g, cudaStream_t st)
 {
-    CUtensorMap ta, tb, to;
+    CUtensorMap ta, tb, to, txb;
     int rc = make_tmap(h, &ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.a, (uint64_t)g.M, (uint64_t)g.K,
                        BM, BK);
     if (rc) return rc;
@@ -339,14 +395,21 @@ int launch_t(VgHandle *h, const GemmArgs &g, cudaStream_t st)
         rc = make_tmap(h, &to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.out, (uint64_t)g.M,
                        (uint64_t)g.N, 32, 64);
     if (rc) return rc;
+    txb = to;
+    if (EPI == VG_EPI_BIAS_RESID_F32 && LNF) {
+        rc = make_tmap(h, &txb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.xb_out, (uint64_t)g.M,
+                       (uint64_t)g.N, 32, 64);
+        if (rc) return rc;
+    }
+    using Cfg = EpiCfg<EPI, LNF>;
     static bool attr_set = false;
     if (!attr_set) {
-        VG_CUDA_CHECK(h, cudaFuncSetAttribute(gemm2_kernel<EPI>,
+        VG_CUDA_CHECK(h, cudaFuncSetAttribute(gemm2_kernel<EPI, LNF>,
                                               cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)SMEM_BYTES));
+                                              (int)Cfg::kSmem));
         attr_set = true;
     }
-    Params p{g.bias, g.M, g.N, g.K};
+    Params p{g.bias, g.colsum, g.stats, g.M, g.N, g.K};
     const int64_t tiles = ((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / BN);
     const int max_clusters = h->num_sms / 2;
     const int clusters = (int)(tiles < max_clusters ? tiles : max_clusters);
@@ -354,7 +417,7 @@ int launch_t(VgHandle *h, const GemmArgs &g, cudaStream_t st)
                      : EPI == VG_EPI_BIAS_QGELU_BF16 ? VG_K_GEMM_FC
                      : (g.K == kMlp ? VG_K_GEMM_PROJ : VG_K_GEMM_OUT);
     VgProfScope prof(h, kind, 2.0 * (double)g.M * g.N * (double)g.K, st);
-    gemm2_kernel<EPI><<<2 * clusters, EpiCfg<EPI>::kThreads, SMEM_BYTES, st>>>(ta, tb, to, p);
+    gemm2_kernel<EPI, LNF><<<2 * clusters, Cfg::kThreads, Cfg::kSmem, st>>>(ta, tb, to, txb, p);
     VG_LAUNCH_CHECK(h);
     return VG_OK;
 }
@@ -363,10 +426,24 @@ int launch_t(VgHandle *h, const GemmArgs &g, cudaStream_t st)
 
 int launch_gemm_2cta(VgHandle *h, const GemmArgs &g, cudaStream_t st)
 {
+    const bool lnf = g.stats != nullptr;
+    if (lnf && g.epilogue != VG_EPI_BIAS_RESID_F32 && !g.colsum) {
+        VG_SET_ERR(h, "gemm2: LayerNorm-folded epilogue needs colsum");
+        return VG_EINVAL;
+    }
+    if (lnf && g.epilogue == VG_EPI_BIAS_RESID_F32 && (!g.xb_out || g.N != kWidth)) {
+        VG_SET_ERR(h, "gemm2: fused residual epilogue needs xb_out and N = 768");
+        return VG_EINVAL;
+    }
     switch (g.epilogue) {
-        case VG_EPI_BIAS_BF16: return launch_t<VG_EPI_BIAS_BF16>(h, g, st);
-        case VG_EPI_BIAS_QGELU_BF16: return launch_t<VG_EPI_BIAS_QGELU_BF16>(h, g, st);
-        case VG_EPI_BIAS_RESID_F32: return launch_t<VG_EPI_BIAS_RESID_F32>(h, g, st);
+        case VG_EPI_BIAS_BF16:
+            return lnf ? launch_t<VG_EPI_BIAS_BF16, true>(h, g, st) : launch_t<VG_EPI_BIAS_BF16, false>(h, g, st);
+        case VG_EPI_BIAS_QGELU_BF16:
+            return lnf ? launch_t<VG_EPI_BIAS_QGELU_BF16, true>(h, g, st)
+                       : launch_t<VG_EPI_BIAS_QGELU_BF16, false>(h, g, st);
+        case VG_EPI_BIAS_RESID_F32:
+            return lnf ? launch_t<VG_EPI_BIAS_RESID_F32, true>(h, g, st)
+                       : launch_t<VG_EPI_BIAS_RESID_F32, false>(h, g, st);
     }
     VG_SET_ERR(h, "gemm2: unsupported epilogue %d", g.epilogue);
     return VG_EINVAL;

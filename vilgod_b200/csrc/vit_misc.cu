@@ -83,7 +83,9 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const float *__rest
 __global__ void __launch_bounds__(256) ln_pre_kernel(float *__restrict__ x,
                                                      const float *__restrict__ table,
                                                      const float *__restrict__ w,
-                                                     const float *__restrict__ b, int64_t rows)
+                                                     const float *__restrict__ b, int64_t rows,
+                                                     __nv_bfloat16 *__restrict__ xb,
+                                                     float *__restrict__ stats)
 {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -94,6 +96,20 @@ __global__ void __launch_bounds__(256) ln_pre_kernel(float *__restrict__ x,
     float4 *dst = reinterpret_cast<float4 *>(x + row * kWidth);
 #pragma unroll
     for (int i = 0; i < 6; ++i) dst[lane + 32 * i] = r.v[i];
+    if (xb) {   // LayerNorm-folded tower: bf16 copy of the residual + row sum / sum of squares
+        uint2 *db = reinterpret_cast<uint2 *>(xb + row * kWidth);
+        float sum = 0.0f, sq = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            db[lane + 32 * i] = make_uint2(pack_bf16x2(r.v[i].x, r.v[i].y), pack_bf16x2(r.v[i].z, r.v[i].w));
+            sum += (r.v[i].x + r.v[i].y) + (r.v[i].z + r.v[i].w);
+            sq += (r.v[i].x * r.v[i].x + r.v[i].y * r.v[i].y) + (r.v[i].z * r.v[i].z + r.v[i].w * r.v[i].w);
+        }
+        sum = warp_sum(sum);
+        sq = warp_sum(sq);
+        if (lane < 3)   // [row][3 column tiles][sum, sum of squares]: everything in tile slot 0
+            reinterpret_cast<float2 *>(stats + 6 * row)[lane] = lane == 0 ? make_float2(sum, sq) : make_float2(0.f, 0.f);
+    }
 }
 
 // One CTA (256 threads) per image: ln_post(CLS) -> @proj -> /|f| -> logit_scale * f.T^T -> softmax
@@ -276,6 +292,37 @@ __global__ void fold_patch_kernel(const float *__restrict__ conv1, __nv_bfloat16
     }
     if (k == 0) b_eff[o] = (float)red[0];
 }
+// LayerNorm folded into the following linear layer:
+//   W'[n][k] = bf16(scale_n * gamma_k * W[n][k]),  colsum_n = sum_k W'[n][k] (of the ROUNDED values,
+//   i.e. exactly what the tensor core sums),  c_n = scale_n * (sum_k beta_k W[n][k] + b_n)
+// scale_n = `scale` for n < scaled_rows (the 1/sqrt(64) query scale), 1 otherwise.
+__global__ void fold_ln_kernel(const float *__restrict__ W, const float *__restrict__ bias,
+                               const float *__restrict__ gamma, const float *__restrict__ beta,
+                               int K, int scaled_rows, float scale, __nv_bfloat16 *__restrict__ Wf,
+                               float *__restrict__ colsum, float *__restrict__ cvec)
+{
+    const int n = blockIdx.x, t = threadIdx.x;
+    const float sc = n < scaled_rows ? scale : 1.0f;
+    __shared__ double red[2][256];
+    double s = 0.0, c = 0.0;
+    for (int k = t; k < K; k += 256) {
+        const float wv = W[(size_t)n * K + k];
+        const __nv_bfloat16 wf = __float2bfloat16_rn(sc * gamma[k] * wv);
+        Wf[(size_t)n * K + k] = wf;
+        s += (double)__bfloat162float(wf);
+        c += (double)beta[k] * (double)wv;
+    }
+    red[0][t] = s; red[1][t] = c;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+        if (t < o) { red[0][t] += red[0][t + o]; red[1][t] += red[1][t + o]; }
+        __syncthreads();
+    }
+    if (t == 0) {
+        colsum[n] = (float)red[0][0];
+        cvec[n] = sc * (float)(red[1][0] + (double)bias[n]);
+    }
+}
 __global__ void patch_table_kernel(const float *__restrict__ cls, const float *__restrict__ pos,
                                    const float *__restrict__ b_eff, float *__restrict__ table)
 {
@@ -295,13 +342,14 @@ int launch_layernorm_bf16(VgHandle *h, const float *x, const float *w, const flo
     return VG_OK;
 }
 
-int launch_ln_pre(VgHandle *h, float *x, int64_t B, cudaStream_t st)
+int launch_ln_pre(VgHandle *h, float *x, int64_t B, __nv_bfloat16 *xb, float *stats, cudaStream_t st)
 {
     const int64_t rows = B * kTokens;
     if (rows <= 0) return VG_OK;
     VgProfScope prof(h, VG_K_LN_PRE, (double)rows * kWidth * 8.0, st);
     ln_pre_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, h->vit.patch_bias_pos,
-                                                              h->vit.ln_pre_w, h->vit.ln_pre_b, rows);
+                                                              h->vit.ln_pre_w, h->vit.ln_pre_b, rows,
+                                                              xb, stats);
     VG_LAUNCH_CHECK(h);
     return VG_OK;
 }
@@ -346,7 +394,9 @@ int convert_weights(VgHandle *h, const VgVitWeights *w, cudaStream_t st)
     size_t o_layer[kLayers];
     const size_t layer_bytes_w = (n_qkv + n_out + 2 * n_fc) * 2;
     const size_t layer_floats = 3 * kWidth + kWidth + kMlp + kWidth + 4 * kWidth;
-    for (int l = 0; l < kLayers; ++l) o_layer[l] = take(layer_bytes_w + layer_floats * 4 + 4096);
+    const size_t fold_bytes = (n_qkv + n_fc) * 2 + (size_t)(2 * 3 * kWidth + 2 * kMlp) * 4;
+    for (int l = 0; l < kLayers; ++l)
+        o_layer[l] = take(layer_bytes_w + layer_floats * 4 + fold_bytes + 4096);
     if (h->arena) { cudaFree(h->arena); h->arena = nullptr; }
     VG_CUDA_CHECK(h, cudaMalloc(&h->arena, bytes));
     h->arena_bytes = bytes;
@@ -394,6 +444,12 @@ int convert_weights(VgHandle *h, const VgVitWeights *w, cudaStream_t st)
         t.ln1_b = f; f += kWidth;
         t.ln2_w = f; f += kWidth;
         t.ln2_b = f; f += kWidth;
+        t.s_qkv = f; f += 3 * kWidth;
+        t.c_qkv = f; f += 3 * kWidth;
+        t.s_fc = f; f += kMlp;
+        t.c_fc = f; f += kMlp;
+        t.wf_qkv = reinterpret_cast<__nv_bfloat16 *>(f);
+        t.wf_fc = t.wf_qkv + n_qkv;
         // 1/sqrt(head_dim) = 0.125 folded into the q rows (exact: power of two)
         cvt(s.attn_in_proj_weight, t.w_qkv, n_qkv, (size_t)kWidth * kWidth, 0.125f);
         f32_scale_prefix_kernel<<<(3 * kWidth + 255) / 256, 256, 0, st>>>(
@@ -409,6 +465,12 @@ int convert_weights(VgHandle *h, const VgVitWeights *w, cudaStream_t st)
         VG_CUDA_CHECK(h, cpy(t.ln1_b, s.ln_1_bias, kWidth));
         VG_CUDA_CHECK(h, cpy(t.ln2_w, s.ln_2_weight, kWidth));
         VG_CUDA_CHECK(h, cpy(t.ln2_b, s.ln_2_bias, kWidth));
+        fold_ln_kernel<<<3 * kWidth, 256, 0, st>>>(s.attn_in_proj_weight, s.attn_in_proj_bias,
+                                                   s.ln_1_weight, s.ln_1_bias, kWidth, kWidth, 0.125f,
+                                                   t.wf_qkv, t.s_qkv, t.c_qkv);
+        fold_ln_kernel<<<kMlp, 256, 0, st>>>(s.mlp_c_fc_weight, s.mlp_c_fc_bias, s.ln_2_weight,
+                                             s.ln_2_bias, kWidth, 0, 1.0f, t.wf_fc, t.s_fc, t.c_fc);
+        h->launches += 2;
     }
     VG_CUDA_CHECK(h, cudaGetLastError());
     VG_CUDA_CHECK(h, cudaStreamSynchronize(st));
