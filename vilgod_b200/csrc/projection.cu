@@ -419,21 +419,27 @@ __global__ void __launch_bounds__(NT, 2) projection_kernel(const ProjParams P)
         {
             const int vlo = max(ylo - 3, 0), vhi = min(yhi + 1, R - 1);
             const int y0 = vlo + warp * CH;
-            float4 h[CH + 4];
+            const bool active = y0 <= vhi && lane < R / 4;      // idle chunks only keep the barrier
+            float4 o[CH];
+            if (active) {
+                float4 h[CH + 4];
 #pragma unroll
-            for (int k = 0; k < CH + 4; ++k) {
-                const int y = y0 - 1 + k;
-                h[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (lane < R / 4 && y0 <= vhi && y >= 0 && y < R)
-                    h[k] = reinterpret_cast<const float4 *>(sm.G + y * R)[lane];
+                for (int k = 0; k < CH + 4; ++k) {
+                    const int y = y0 - 1 + k;
+                    h[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (y >= 0 && y < R) h[k] = reinterpret_cast<const float4 *>(sm.G + y * R)[lane];
+                }
+#pragma unroll
+                for (int k = 0; k < CH; ++k) {
+                    o[k] = max4(max4(max4(h[k], h[k + 1]), max4(h[k + 2], h[k + 3])), h[k + 4]);
+                    if (y0 + k >= Q) o[k] = make_float4(0.f, 0.f, 0.f, 0.f);   // rows 110, 111: padding
+                }
             }
-            __syncthreads();
+            __syncthreads();      // every load of the in-place pass precedes every store
+            if (active) {
 #pragma unroll
-            for (int k = 0; k < CH; ++k) {
-                const int y = y0 + k;
-                float4 o = max4(max4(max4(h[k], h[k + 1]), max4(h[k + 2], h[k + 3])), h[k + 4]);
-                if (y >= Q) o = make_float4(0.f, 0.f, 0.f, 0.f);   // rows 110, 111: padding
-                if (lane < R / 4 && y <= vhi) reinterpret_cast<float4 *>(sm.G + y * R)[lane] = o;
+                for (int k = 0; k < CH; ++k)
+                    if (y0 + k <= vhi) reinterpret_cast<float4 *>(sm.G + (y0 + k) * R)[lane] = o[k];
             }
         }
         __syncthreads();
