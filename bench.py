@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-clusters", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=20240807)
+    ap.add_argument("--operand-dtype", default="bf16", choices=["bf16", "f16"],
+                    help="GEMM operand type: bf16 (BASELINE.json's config) or fp16 (the reference's GPU dtype)")
     return ap.parse_args()
 
 
@@ -205,7 +207,7 @@ def run_ours(a):
     V = a.views
     total_points = int(off_np[-1])
 
-    eng = Engine(num_views=V)
+    eng = Engine(num_views=V, operand_dtype=a.operand_dtype)
     eng.load_vit_weights(vw.random_init_visual_state_dict(1234))
     text = vw.synthetic_text_features(24)
     eng.set_text_features(text)
@@ -354,7 +356,7 @@ def run_ours(a):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": ms_total / a.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": a.operand_dtype, "data": "synthetic",
             "config": {"workload": workload_name(a), "clusters_per_rank": C, "views": V,
                        "images_per_step_per_rank": C * V, "points_per_rank": total_points,
                        "weights": "random-init ViT-B/16 (seed 1234, fp16-rounded like build_model)",

@@ -122,6 +122,10 @@ VG_API int vg_create(const VgConfig *cfg, VgHandle **out);
 VG_API void vg_destroy(VgHandle *h);
 VG_API const char *vg_last_error(const VgHandle *h);
 VG_API int vg_abi_version(void);
+/* GEMM operand type this build of the library computes in: 0 = bf16 (libvilgod_b200.so),
+ * 1 = fp16 (libvilgod_b200_f16.so, the reference's own GPU dtype).  Every buffer documented as
+ * "bf16" below holds that type.  Accumulation / residual stream / soft-max are fp32 in both. */
+VG_API int vg_operand_dtype(void);
 
 VG_API int vg_load_vit_weights(VgHandle *h, const VgVitWeights *w, void *stream);
 /* d_text: [P,512] fp32 L2-normalised prompt embeddings (device).  class_map: HOST int32 [P] giving

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.fixture(scope="module")
 def lib_path():
     from vilgod_b200 import build
-    return build.build_library()
+    return build.build_all()[0]
 
 
 def declared_symbols():
@@ -38,8 +38,9 @@ def test_library_exports_every_declared_symbol(lib_path):
 def test_ctypes_binding_covers_the_header(lib_path):
     from vilgod_b200 import _lib
     assert sorted(_lib.SYMBOLS) == declared_symbols()
-    lib = _lib.load()
-    assert lib.vg_abi_version() == _lib.VG_ABI_VERSION
+    for dt, code in (("bf16", 0), ("f16", 1)):
+        lib = _lib.load(dt)
+        assert lib.vg_abi_version() == _lib.VG_ABI_VERSION and lib.vg_operand_dtype() == code
 
 
 def test_struct_layouts_match_the_header():

@@ -111,6 +111,21 @@ def test_rotation_modes(engines):
         assert np.array_equal(out["u8"].cpu().numpy().reshape(u8_o.shape), u8_o)
 
 
+def test_fp16_operand_build_emits_the_same_pixels(golden):
+    """The fp16-operand library differs from the bf16 one only in the tile element type."""
+    from vilgod_b200.engine import Engine
+    g = golden["projection"]
+    e = Engine(num_views=6, operand_dtype="f16")
+    try:
+        out = e.project(g["points"], g["offsets"], want_u8=True)
+        assert out["tiles"].dtype == torch.float16
+        assert torch.equal(tiles_to_u8(out["tiles"]), out["u8"])
+        diff = np.abs(out["u8"].cpu().numpy().reshape(g["u8_6"].shape).astype(int) - g["u8_6"].astype(int))
+        assert diff.max() <= 1 and (diff != 0).mean() < 3e-3
+    finally:
+        e.close()
+
+
 def test_degenerate_and_edge_clusters(engines):
     eng = engines(4)
     a = np.random.default_rng(0).normal(size=(50, 3)).astype(np.float32)

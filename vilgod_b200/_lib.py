@@ -10,6 +10,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libvilgod_b200.so")
+LIB_PATHS = {"bf16": LIB_PATH, "f16": os.path.join(HERE, "lib", "libvilgod_b200_f16.so")}
 
 VG_ABI_VERSION = 1
 VG_MAX_VIEWS = 16
@@ -66,6 +67,7 @@ class VgVitDebug(C.Structure):
 # every symbol include/vilgod_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "vg_abi_version": (C.c_int, []),
+    "vg_operand_dtype": (C.c_int, []),
     "vg_create": (C.c_int, [C.POINTER(VgConfig), C.POINTER(C.c_void_p)]),
     "vg_destroy": (None, [C.c_void_p]),
     "vg_last_error": (C.c_char_p, [C.c_void_p]),
@@ -93,25 +95,29 @@ SYMBOLS = {
                                     C.c_void_p, C.c_void_p]),
 }
 
-_lib = None
+_libs = {}
 
 
-def load():
-    """dlopen the library and bind every declared symbol (raises if one is missing)."""
-    global _lib
-    if _lib is None:
-        if not os.path.exists(LIB_PATH):
+def load(operand_dtype="bf16"):
+    """dlopen the bf16- or fp16-operand build and bind every declared symbol (raises if missing)."""
+    if operand_dtype not in LIB_PATHS:
+        raise ValueError(f"operand_dtype must be one of {sorted(LIB_PATHS)}")
+    if operand_dtype not in _libs:
+        path = LIB_PATHS[operand_dtype]
+        if not os.path.exists(path):
             raise RuntimeError(
-                f"{LIB_PATH} not built: run `python -m vilgod_b200.build` (needs nvcc, sm_100a). "
+                f"{path} not built: run `python -m vilgod_b200.build` (needs nvcc, sm_100a). "
                 "vilgod_b200 has no CPU fallback.")
-        lib = C.CDLL(LIB_PATH)
+        lib = C.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
         if lib.vg_abi_version() != VG_ABI_VERSION:
-            raise RuntimeError("libvilgod_b200.so ABI version mismatch; rebuild")
-        _lib = lib
-    return _lib
+            raise RuntimeError(f"{os.path.basename(path)} ABI version mismatch; rebuild")
+        if lib.vg_operand_dtype() != (1 if operand_dtype == "f16" else 0):
+            raise RuntimeError(f"{os.path.basename(path)} was built for another operand dtype")
+        _libs[operand_dtype] = lib
+    return _libs[operand_dtype]
 
 
 class VilgodError(RuntimeError):

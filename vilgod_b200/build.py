@@ -10,7 +10,8 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
-LIB_PATH = os.path.join(OUT_DIR, "libvilgod_b200.so")
+LIB_PATH = os.path.join(OUT_DIR, "libvilgod_b200.so")           # bf16 GEMM operands (default)
+LIB_PATH_F16 = os.path.join(OUT_DIR, "libvilgod_b200_f16.so")   # fp16 GEMM operands (-DVG_OPERAND_F16)
 SOURCES = ["api.cu", "projection.cu", "gemm_tcgen05.cu", "gemm_tcgen05_2cta.cu", "attention.cu",
            "attention_tcgen05.cu",
            "vit_misc.cu"]
@@ -31,16 +32,18 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False):
+def build_library(force=False, verbose=False, f16=False):
     os.makedirs(OUT_DIR, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
     objs, jobs = [], []
+    lib_path = LIB_PATH_F16 if f16 else LIB_PATH
     for s in SOURCES:
         src = os.path.join(CSRC, s)
-        obj = os.path.join(OUT_DIR, s.replace(".cu", ".o"))
+        obj = os.path.join(OUT_DIR, s.replace(".cu", "_f16.o" if f16 else ".o"))
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs):
-            cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            cmd = ([_nvcc()] + NVCC_FLAGS + (["-DVG_OPERAND_F16=1"] if f16 else [])
+                   + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj])
             jobs.append(cmd)
 
     def run(cmd):
@@ -54,10 +57,14 @@ def build_library(force=False, verbose=False):
             for log in ex.map(run, jobs):
                 if verbose and log:
                     print(log, file=sys.stderr)
-    if jobs or not os.path.exists(LIB_PATH):
-        run([_nvcc(), "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
-    return LIB_PATH
+    if jobs or not os.path.exists(lib_path):
+        run([_nvcc(), "-shared", "-o", lib_path] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    return lib_path
+
+
+def build_all(force=False, verbose=False):
+    return [build_library(force, verbose, f16=False), build_library(force, verbose, f16=True)]
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_all(force="--force" in sys.argv, verbose="-v" in sys.argv))

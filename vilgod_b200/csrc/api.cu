@@ -20,9 +20,9 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct EncodeBuffers {
     float *x;               // residual stream fp32 [M,768]
-    __nv_bfloat16 *y;       // attention output (A of out-proj) [M,768]; LayerNorm output when unfused
-    __nv_bfloat16 *big;     // qkv [M,2304] / MLP hidden [M,3072]
-    __nv_bfloat16 *xb;      // bf16 copy of the residual stream (A of the LayerNorm-folded GEMMs)
+    op_t *y;       // attention output (A of out-proj) [M,768]; LayerNorm output when unfused
+    op_t *big;     // qkv [M,2304] / MLP hidden [M,3072]
+    op_t *xb;      // bf16 copy of the residual stream (A of the LayerNorm-folded GEMMs)
     float *stats;           // row sum / sum of squares of the residual stream [M,3,2]
 };
 
@@ -32,11 +32,11 @@ EncodeBuffers carve(void *ws, int64_t chunk)
     EncodeBuffers b;
     b.x = reinterpret_cast<float *>(p);
     p += align_up((size_t)chunk * kTokens * kWidth * 4, 1024);
-    b.y = reinterpret_cast<__nv_bfloat16 *>(p);
+    b.y = reinterpret_cast<op_t *>(p);
     p += align_up((size_t)chunk * kTokens * kWidth * 2, 1024);
-    b.big = reinterpret_cast<__nv_bfloat16 *>(p);
+    b.big = reinterpret_cast<op_t *>(p);
     p += align_up((size_t)chunk * kTokens * kMlp * 2, 1024);
-    b.xb = reinterpret_cast<__nv_bfloat16 *>(p);
+    b.xb = reinterpret_cast<op_t *>(p);
     p += align_up((size_t)chunk * kTokens * kWidth * 2, 1024);
     b.stats = reinterpret_cast<float *>(p);
     return b;
@@ -52,7 +52,7 @@ size_t encode_bytes(int64_t chunk)
 }
 
 // the visual tower on `n` images whose patch-major tiles start at `tiles`
-int encode_chunk(VgHandle *h, const __nv_bfloat16 *tiles, int64_t n, const EncodeBuffers &eb,
+int encode_chunk(VgHandle *h, const op_t *tiles, int64_t n, const EncodeBuffers &eb,
                  float *probs, int32_t *top1, float *feats, float *logits, const VgVitDebug *dbg,
                  cudaStream_t st)
 {
@@ -119,6 +119,8 @@ int encode_chunk(VgHandle *h, const __nv_bfloat16 *tiles, int64_t n, const Encod
 extern "C" {
 
 int vg_abi_version(void) { return VG_ABI_VERSION; }
+
+int vg_operand_dtype(void) { return kOperandDtype; }
 
 int vg_create(const VgConfig *cfg, VgHandle **out)
 {
@@ -257,7 +259,7 @@ int vg_project(VgHandle *h, const float *d_points, const int32_t *d_offsets, int
         VG_SET_ERR(h, "vg_project: null points/offsets or negative cluster count");
         return VG_EINVAL;
     }
-    return launch_projection(h, d_points, d_offsets, C, static_cast<__nv_bfloat16 *>(d_tiles), d_u8,
+    return launch_projection(h, d_points, d_offsets, C, static_cast<op_t *>(d_tiles), d_u8,
                              d_status, dbg, static_cast<cudaStream_t>(stream));
 }
 
@@ -283,7 +285,7 @@ int vg_encode_score(VgHandle *h, const void *d_tiles, int64_t B, float *d_probs,
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const EncodeBuffers eb = carve(d_ws, chunk);
-    const __nv_bfloat16 *tiles = static_cast<const __nv_bfloat16 *>(d_tiles);
+    const op_t *tiles = static_cast<const op_t *>(d_tiles);
     for (int64_t i = 0; i < B; i += chunk) {
         const int64_t n = B - i < chunk ? B - i : chunk;
         int rc = encode_chunk(h, tiles + i * VG_TILE_ELEMS, n, eb,
@@ -332,7 +334,7 @@ int vg_classify(VgHandle *h, const float *d_points, const int32_t *d_offsets, in
                    ws_bytes, need(cc), (long long)cc);
         return VG_EWORKSPACE;
     }
-    __nv_bfloat16 *tiles = static_cast<__nv_bfloat16 *>(d_ws);
+    op_t *tiles = static_cast<op_t *>(d_ws);
     char *enc_ws = static_cast<char *>(d_ws) + align_up((size_t)cc * V * kTileBytesPerImage, 1024);
     const EncodeBuffers eb = carve(enc_ws, cc * V);
     const int P = h->num_prompts;
@@ -355,7 +357,7 @@ int vg_test_gemm(VgHandle *h, const void *d_a, const void *d_w, const float *d_b
 {
     if (!h || !d_a || !d_w || !d_bias || !d_out) return VG_EINVAL;
     if (epilogue < 0 || epilogue > VG_EPI_BIAS_RESID_F32) return VG_EINVAL;
-    GemmArgs g{static_cast<const __nv_bfloat16 *>(d_a), static_cast<const __nv_bfloat16 *>(d_w),
+    GemmArgs g{static_cast<const op_t *>(d_a), static_cast<const op_t *>(d_w),
                d_bias, d_out, M, N, K, epilogue};
     return launch_gemm(h, g, static_cast<cudaStream_t>(stream));
 }
@@ -363,15 +365,15 @@ int vg_test_gemm(VgHandle *h, const void *d_a, const void *d_w, const float *d_b
 int vg_test_attention(VgHandle *h, const void *d_qkv, int64_t B, void *d_out, void *stream)
 {
     if (!h || !d_qkv || !d_out) return VG_EINVAL;
-    return launch_attention(h, static_cast<const __nv_bfloat16 *>(d_qkv), B,
-                            static_cast<__nv_bfloat16 *>(d_out), static_cast<cudaStream_t>(stream));
+    return launch_attention(h, static_cast<const op_t *>(d_qkv), B,
+                            static_cast<op_t *>(d_out), static_cast<cudaStream_t>(stream));
 }
 
 int vg_test_layernorm(VgHandle *h, const float *d_x, const float *d_w, const float *d_b,
                       int64_t rows, void *d_y, void *stream)
 {
     if (!h || !d_x || !d_w || !d_b || !d_y) return VG_EINVAL;
-    return launch_layernorm_bf16(h, d_x, d_w, d_b, rows, static_cast<__nv_bfloat16 *>(d_y),
+    return launch_layernorm_bf16(h, d_x, d_w, d_b, rows, static_cast<op_t *>(d_y),
                                  static_cast<cudaStream_t>(stream));
 }
 

@@ -202,13 +202,15 @@ attention_kernel(const __nv_bfloat16 *__restrict__ qkv, __nv_bfloat16 *__restric
 
 }  // namespace
 
-int launch_attention(VgHandle *h, const __nv_bfloat16 *qkv, int64_t B, __nv_bfloat16 *out,
+int launch_attention(VgHandle *h, const op_t *qkv_op, int64_t B, op_t *out_op,
                      cudaStream_t st)
 {
     if (B <= 0) return VG_OK;
     // production path: tcgen05 kernel (attention_tcgen05.cu); VG_ATTN_V1=1 selects this mma.sync one
-    static const bool force_v1 = getenv("VG_ATTN_V1") != nullptr;
-    if (!force_v1) return launch_attention_tc(h, qkv, B, out, st);
+    static const bool force_v1 = getenv("VG_ATTN_V1") != nullptr && kOperandDtype == 0;   // mma.sync kernel is bf16 only
+    if (!force_v1) return launch_attention_tc(h, qkv_op, B, out_op, st);
+    const __nv_bfloat16 *qkv = reinterpret_cast<const __nv_bfloat16 *>(qkv_op);
+    __nv_bfloat16 *out = reinterpret_cast<__nv_bfloat16 *>(out_op);
     static bool attr_set = false;
     if (!attr_set) {
         VG_CUDA_CHECK(h, cudaFuncSetAttribute(attention_kernel,

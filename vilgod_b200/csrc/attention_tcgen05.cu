@@ -125,11 +125,6 @@ __device__ __forceinline__ float ex2_approx(float x)
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b)
-{
-    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t *>(&t);
-}
 // MN-major B operand (V stored [key][dim], 128-byte rows, SWIZZLE_128B): 8-key groups 1024 B apart
 __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr)
 {
@@ -143,11 +138,11 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr)
 }
 __host__ __device__ constexpr uint32_t idesc_bf16(uint32_t M, uint32_t N, uint32_t b_mn_major)
 {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+    return (1u << 4) | (kOpFormat << 7) | (kOpFormat << 10) | (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, __nv_bfloat16 *__restrict__ out,
+attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, op_t *__restrict__ out,
                     int64_t num_items, long long *trace)
 {
     // optional timeline trace (test hook): CTA 0 records clock64 stamps of its first 8 items
@@ -322,7 +317,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, __nv_bfloat16 *
                                 const float p0 = ex2_approx(t0);
                                 const float p1 = c0 + 1 < L ? ex2_approx(t1) : 0.0f;
                                 sum2 = add2(sum2, pack2(p0, p1));
-                                pk[j] = pack_bf16(p0, p1);
+                                pk[j] = pack_op(p0, p1);
                             }
                             tmem_st_x8(t_slot + (uint32_t)p_col(ch), pk);
                         }
@@ -376,10 +371,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, __nv_bfloat16 *
                     for (int q = 0; q < 8; ++q) {
                         const uint32_t *src = q < 4 ? &o0[8 * q] : &o1[8 * (q - 4)];
                         dst[q] = make_uint4(
-                            pack_bf16(__uint_as_float(src[0]) * inv_sum, __uint_as_float(src[1]) * inv_sum),
-                            pack_bf16(__uint_as_float(src[2]) * inv_sum, __uint_as_float(src[3]) * inv_sum),
-                            pack_bf16(__uint_as_float(src[4]) * inv_sum, __uint_as_float(src[5]) * inv_sum),
-                            pack_bf16(__uint_as_float(src[6]) * inv_sum, __uint_as_float(src[7]) * inv_sum));
+                            pack_op(__uint_as_float(src[0]) * inv_sum, __uint_as_float(src[1]) * inv_sum),
+                            pack_op(__uint_as_float(src[2]) * inv_sum, __uint_as_float(src[3]) * inv_sum),
+                            pack_op(__uint_as_float(src[4]) * inv_sum, __uint_as_float(src[5]) * inv_sum),
+                            pack_op(__uint_as_float(src[6]) * inv_sum, __uint_as_float(src[7]) * inv_sum));
                     }
                 }
             }
@@ -397,7 +392,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, __nv_bfloat16 *
 
 }  // namespace
 
-int launch_attention_tc(VgHandle *h, const __nv_bfloat16 *qkv, int64_t B, __nv_bfloat16 *out,
+int launch_attention_tc(VgHandle *h, const op_t *qkv, int64_t B, op_t *out,
                         cudaStream_t st)
 {
     if (B <= 0) return VG_OK;
@@ -411,7 +406,7 @@ int launch_attention_tc(VgHandle *h, const __nv_bfloat16 *qkv, int64_t B, __nv_b
     const cuuint64_t gstride[2] = {3 * kWidth * 2, (cuuint64_t)L * 3 * kWidth * 2};
     const cuuint32_t box[3] = {HD, LP, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16 *>(qkv),
+    CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<op_t *>(qkv),
                         gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

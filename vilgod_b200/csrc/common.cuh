@@ -3,6 +3,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -13,6 +14,34 @@
 #include "../../include/vilgod_b200.h"
 
 namespace vg {
+
+// GEMM operand type of the whole library, fixed at build time: bf16 (default, libvilgod_b200.so) or
+// fp16 (-DVG_OPERAND_F16, libvilgod_b200_f16.so -- the reference's own GPU dtype; its weights are
+// exactly representable in fp16, third_party/CLIP/clip/model.py:375-396).  Accumulation, residual
+// stream, LayerNorm statistics and soft-max are fp32 in both builds.
+#ifdef VG_OPERAND_F16
+typedef __half op_t;
+constexpr uint32_t kOpFormat = 0;   // tcgen05 instruction-descriptor a/b format: F16
+constexpr int kOperandDtype = 1;
+__device__ __forceinline__ uint32_t pack_op(float a, float b)
+{
+    __half2 t = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&t);
+}
+__device__ __forceinline__ op_t to_op(float v) { return __float2half_rn(v); }
+__device__ __forceinline__ float from_op(op_t v) { return __half2float(v); }
+#else
+typedef __nv_bfloat16 op_t;
+constexpr uint32_t kOpFormat = 1;   // BF16
+constexpr int kOperandDtype = 0;
+__device__ __forceinline__ uint32_t pack_op(float a, float b)
+{
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&t);
+}
+__device__ __forceinline__ op_t to_op(float v) { return __float2bfloat16_rn(v); }
+__device__ __forceinline__ float from_op(op_t v) { return __bfloat162float(v); }
+#endif
 
 constexpr int kWidth = VG_VIT_WIDTH;     // 768
 constexpr int kTokens = VG_VIT_TOKENS;   // 197
@@ -26,17 +55,17 @@ constexpr int kPatchK = 256;             // folded patch-embed K (3 identical ch
 constexpr int kMaxPrompts = 64;
 
 struct LayerDev {
-    __nv_bfloat16 *w_qkv, *w_out, *w_fc, *w_proj;   // [N,K] row-major bf16
+    op_t *w_qkv, *w_out, *w_fc, *w_proj;   // [N,K] row-major bf16
     float *b_qkv, *b_out, *b_fc, *b_proj;           // fp32
     // LayerNorm-folded variants of the two GEMMs that consume a LayerNorm output:
     //   W' = W o gamma (bf16), colsum_n = sum_k W'[n][k], c_n = sum_k beta_k W[n][k] + b_n
-    __nv_bfloat16 *wf_qkv, *wf_fc;
+    op_t *wf_qkv, *wf_fc;
     float *s_qkv, *c_qkv, *s_fc, *c_fc;
     float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
 };
 
 struct VitDev {
-    __nv_bfloat16 *w_patch;   // [768,256] folded patch embedding
+    op_t *w_patch;   // [768,256] folded patch embedding
     float *patch_bias_pos;    // [197,768]: row 0 = cls + pos[0]; row 1+p = b_eff + pos[1+p]
     float *ln_pre_w, *ln_pre_b, *ln_post_w, *ln_post_b;
     float *proj;              // [768,512] fp32
@@ -124,13 +153,13 @@ namespace vg {
 
 int projection_init(VgHandle *h);   // builds the handle-owned projection tables (vg_create)
 int launch_projection(VgHandle *h, const float *d_points, const int32_t *d_offsets, int32_t C,
-                      __nv_bfloat16 *d_tiles, uint8_t *d_u8, int32_t *d_status,
+                      op_t *d_tiles, uint8_t *d_u8, int32_t *d_status,
                       const VgProjectDebug *dbg, cudaStream_t st);
 
 // D = epilogue(A[M,K] * W[N,K]^T + bias).  a_row_map: optional remap used by the patch-embed.
 struct GemmArgs {
-    const __nv_bfloat16 *a;   // [M,K]
-    const __nv_bfloat16 *w;   // [N,K]
+    const op_t *a;   // [M,K]
+    const op_t *w;   // [N,K]
     const float *bias;        // [N] (or [197,N] table for the patch-embed epilogue)
     void *out;                // bf16 [M,N] or fp32 [M,N] (resid: in/out)
     int64_t M;
@@ -139,20 +168,20 @@ struct GemmArgs {
     // LayerNorm folding (2-CTA kernel only; all null = plain epilogues)
     float *stats = nullptr;            // [M][3][2] per column tile: row sum / sum of squares
     const float *colsum = nullptr;     // [N] sum_k W'[n][k]   (bf16 epilogues consuming `stats`)
-    __nv_bfloat16 *xb_out = nullptr;   // [M][768] bf16 copy of the new residual (residual epilogue)
+    op_t *xb_out = nullptr;   // [M][768] bf16 copy of the new residual (residual epilogue)
 };
 constexpr int kEpiPatch = 3;  // out fp32 x[img*197 + 1 + p][n] = acc + table[1+p][n]
 int launch_gemm(VgHandle *h, const GemmArgs &g, cudaStream_t st);
 int launch_gemm_2cta(VgHandle *h, const GemmArgs &g, cudaStream_t st);   // cta_group::2 path
 
-int launch_attention(VgHandle *h, const __nv_bfloat16 *qkv, int64_t B, __nv_bfloat16 *out,
+int launch_attention(VgHandle *h, const op_t *qkv, int64_t B, op_t *out,
                      cudaStream_t st);
-int launch_attention_tc(VgHandle *h, const __nv_bfloat16 *qkv, int64_t B, __nv_bfloat16 *out,
+int launch_attention_tc(VgHandle *h, const op_t *qkv, int64_t B, op_t *out,
                         cudaStream_t st);   // tcgen05 / TMEM path (attention_tcgen05.cu)
 int launch_layernorm_bf16(VgHandle *h, const float *x, const float *w, const float *b,
-                          int64_t rows, __nv_bfloat16 *y, cudaStream_t st);
+                          int64_t rows, op_t *y, cudaStream_t st);
 // x[img,0,:] = table[0]; then x = LN(x) in place (ln_pre) over all B*197 rows
-int launch_ln_pre(VgHandle *h, float *x, int64_t B, __nv_bfloat16 *xb, float *stats, cudaStream_t st);
+int launch_ln_pre(VgHandle *h, float *x, int64_t B, op_t *xb, float *stats, cudaStream_t st);
 // ln_post on CLS rows -> proj -> L2 norm -> logits -> softmax -> argmax
 int launch_head(VgHandle *h, const float *x, int64_t B, float *probs, int32_t *top1, float *feats,
                 float *logits, cudaStream_t st);

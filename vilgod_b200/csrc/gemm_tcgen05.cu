@@ -48,11 +48,6 @@ __device__ __forceinline__ float quick_gelu(float v)
     return __fdividef(v, 1.0f + __expf(-1.702f * v));
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b)
-{
-    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t *>(&t);
-}
 
 template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -119,7 +114,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(BM, BN);
+            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(BM, BN, kOpFormat);
             int stage = 0, as = 0;
             uint32_t phase = 0, aphase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -179,7 +174,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     const float4 *b4 = reinterpret_cast<const float4 *>(brow + n0);
                     if (EPI == VG_EPI_BIAS_BF16 || EPI == VG_EPI_BIAS_QGELU_BF16) {
                         uint4 *dst = reinterpret_cast<uint4 *>(
-                            reinterpret_cast<__nv_bfloat16 *>(p.out) + orow * p.N + n0);
+                            reinterpret_cast<op_t *>(p.out) + orow * p.N + n0);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             float v[8];
@@ -190,8 +185,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                                 v[j] = __uint_as_float(r[8 * q + j]) + bv[j];
                                 if (EPI == VG_EPI_BIAS_QGELU_BF16) v[j] = quick_gelu(v[j]);
                             }
-                            dst[q] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
-                                                pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                            dst[q] = make_uint4(pack_op(v[0], v[1]), pack_op(v[2], v[3]),
+                                                pack_op(v[4], v[5]), pack_op(v[6], v[7]));
                         }
                     } else {
                         float4 *dst =
@@ -236,7 +231,7 @@ int make_tmap_2d(VgHandle *h, CUtensorMap *map, const void *ptr, uint64_t rows, 
         return VG_ECUDA;
     }
     const cuuint64_t gdim[2] = {cols, rows};
-    const cuuint64_t gstride[1] = {cols * sizeof(__nv_bfloat16)};
+    const cuuint64_t gstride[1] = {cols * sizeof(op_t)};
     const cuuint32_t box[2] = {box_cols, box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), gdim,

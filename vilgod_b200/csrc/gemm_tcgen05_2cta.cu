@@ -69,11 +69,6 @@ __device__ __forceinline__ float quick_gelu(float v)
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * v));
     return v * fmaf(0.5f, t, 0.5f);
 }
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b)
-{
-    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t *>(&t);
-}
 // 16-byte chunk c of row r inside a 1024-byte-aligned SWIZZLE_128B slab
 __device__ __forceinline__ uint32_t slab_off(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
 
@@ -159,7 +154,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         // instructions.  With a lone divergent lane ptxas wraps every UTCHMMA in an ELECT / R2UR
         // waterfall; convergent code keeps descriptors and TMEM addresses in uniform registers.
         if (leader) {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(2 * BM, BN);
+            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(2 * BM, BN, kOpFormat);
             const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
             int stage = 0, as = 0;
             uint32_t phase = 0, aphase = 0;
@@ -251,7 +246,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                             rq += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
                             // bf16 copy: two 32-column chunks share one 64-column slab row (128 B)
                             unsigned char *xb = slab + (4 + ((ch >> 1) & 1)) * SLAB_BYTES;
-                            uint2 pk = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+                            uint2 pk = make_uint2(pack_op(o.x, o.y), pack_op(o.z, o.w));
                             *reinterpret_cast<uint2 *>(xb + slab_off(lane, (ch & 1) * 4 + (q >> 1)) +
                                                        (q & 1) * 8) = pk;
                         }
@@ -325,8 +320,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                             for (int j = 0; j < 8; ++j) v[j] = quick_gelu(v[j]);
                         }
                         *reinterpret_cast<uint4 *>(out + slab_off(lane, q)) =
-                            make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
-                                       pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                            make_uint4(pack_op(v[0], v[1]), pack_op(v[2], v[3]),
+                                       pack_op(v[4], v[5]), pack_op(v[6], v[7]));
                     }
                     ptx::fence_proxy_async();
                     __syncwarp();

@@ -54,7 +54,7 @@ struct ProjParams {
     float gauss[9];
     float obj_ratio, depth_bias, one_plus_bias;
     int32_t rotate_mode;
-    __nv_bfloat16 *tiles;
+    op_t *tiles;
     uint8_t *u8;
     int32_t *status;
     float *dbg_grid;
@@ -222,7 +222,7 @@ __global__ void projection_tables_kernel(ProjTables *t)
         const float v = quant255(__fmaf_rn(c, lh0, __fmul_rn(c, lh1)));
         reinterpret_cast<uint8_t *>(t->bg_u8)[px] = (uint8_t)v;
         const int patch = (oy >> 4) * 14 + (ox >> 4), inner = (oy & 15) * 16 + (ox & 15);
-        reinterpret_cast<__nv_bfloat16 *>(t->bg_tile)[patch * 256 + inner] = __float2bfloat16_rn(v);
+        reinterpret_cast<op_t *>(t->bg_tile)[patch * 256 + inner] = to_op(v);
     }
 }
 
@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(NT, 2) projection_kernel(const ProjParams P)
     // (held in the grid buffer), then out = fma(HI[y0], lh0, HI[y1]*lh1) -- the exact contraction
     // pattern of torch-CPU's separable interpolation on an FMA host.  One warp per output row; rows
     // whose two source rows lie outside [ulo, uhi] are copied from the precomputed background tile.
-    __nv_bfloat16 *tile = P.tiles ? P.tiles + (size_t)b * VG_TILE_ELEMS : nullptr;
+    op_t *tile = P.tiles ? P.tiles + (size_t)b * VG_TILE_ELEMS : nullptr;
     uint8_t *u8 = P.u8 ? P.u8 + (size_t)b * S * S : nullptr;
     const ProjTables *__restrict__ tab = P.tab;
     int cx0 = 0, cx1 = 0;
@@ -597,12 +597,19 @@ __global__ void __launch_bounds__(NT, 2) projection_kernel(const ProjParams P)
                 fb[2 * j + 1] = __float_as_uint(q1);
             }
             if (tile) {
-                // integers 0..255 are exact in bf16: the bf16 pattern is the high half of the fp32
                 uint4 pk;
+#ifdef VG_OPERAND_F16
+                pk.x = pack_op(__uint_as_float(fb[0]), __uint_as_float(fb[1]));
+                pk.y = pack_op(__uint_as_float(fb[2]), __uint_as_float(fb[3]));
+                pk.z = pack_op(__uint_as_float(fb[4]), __uint_as_float(fb[5]));
+                pk.w = pack_op(__uint_as_float(fb[6]), __uint_as_float(fb[7]));
+#else
+                // integers 0..255 are exact in bf16: the bf16 pattern is the high half of the fp32
                 pk.x = __byte_perm(fb[0], fb[1], 0x7632);
                 pk.y = __byte_perm(fb[2], fb[3], 0x7632);
                 pk.z = __byte_perm(fb[4], fb[5], 0x7632);
                 pk.w = __byte_perm(fb[6], fb[7], 0x7632);
+#endif
                 *reinterpret_cast<uint4 *>(tile + patch * 256 + inner) = pk;
             }
             if (u8) {
@@ -636,7 +643,7 @@ int projection_init(VgHandle *h)
 }
 
 int launch_projection(VgHandle *h, const float *d_points, const int32_t *d_offsets, int32_t C,
-                      __nv_bfloat16 *d_tiles, uint8_t *d_u8, int32_t *d_status,
+                      op_t *d_tiles, uint8_t *d_u8, int32_t *d_status,
                       const VgProjectDebug *dbg, cudaStream_t st)
 {
     const VgConfig &cfg = h->cfg;

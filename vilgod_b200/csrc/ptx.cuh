@@ -175,11 +175,11 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr)
 }
 
 // Instruction descriptor for tcgen05.mma.kind::f16: bf16 A/B (both K-major), fp32 accumulate
-__host__ __device__ constexpr uint32_t make_idesc_bf16_f32(uint32_t M, uint32_t N)
+__host__ __device__ constexpr uint32_t make_idesc_bf16_f32(uint32_t M, uint32_t N, uint32_t fmt = 1)
 {
     return (1u << 4)            // c_format  = F32
-           | (1u << 7)          // a_format  = BF16
-           | (1u << 10)         // b_format  = BF16
+           | (fmt << 7)         // a_format  = BF16 (1) / F16 (0)
+           | (fmt << 10)        // b_format
            | (0u << 15)         // a_major   = K
            | (0u << 16)         // b_major   = K
            | ((N >> 3) << 17)   // n_dim

@@ -55,17 +55,13 @@ struct Row768 {
     }
 };
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b)
-{
-    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t *>(&t);
-}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) { return pack_op(a, b); }
 
 __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const float *__restrict__ x,
                                                              const float *__restrict__ w,
                                                              const float *__restrict__ b,
                                                              int64_t rows,
-                                                             __nv_bfloat16 *__restrict__ y)
+                                                             op_t *__restrict__ y)
 {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -84,7 +80,7 @@ __global__ void __launch_bounds__(256) ln_pre_kernel(float *__restrict__ x,
                                                      const float *__restrict__ table,
                                                      const float *__restrict__ w,
                                                      const float *__restrict__ b, int64_t rows,
-                                                     __nv_bfloat16 *__restrict__ xb,
+                                                     op_t *__restrict__ xb,
                                                      float *__restrict__ stats)
 {
     const int lane = threadIdx.x & 31;
@@ -254,11 +250,11 @@ __global__ void vote_kernel(const float *__restrict__ probs, const int32_t *__re
 }
 
 // ---- weight conversion ------------------------------------------------------------------------------
-__global__ void f32_to_bf16_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst,
+__global__ void f32_to_bf16_kernel(const float *__restrict__ src, op_t *__restrict__ dst,
                                    size_t n, size_t scaled_prefix, float scale)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = __float2bfloat16_rn(src[i] * (i < scaled_prefix ? scale : 1.0f));
+    if (i < n) dst[i] = to_op(src[i] * (i < scaled_prefix ? scale : 1.0f));
 }
 __global__ void f32_scale_prefix_kernel(const float *__restrict__ src, float *__restrict__ dst,
                                         size_t n, size_t scaled_prefix, float scale)
@@ -270,7 +266,7 @@ __global__ void f32_scale_prefix_kernel(const float *__restrict__ src, float *__
 // Patch-embed folding.  The three input channels are the same uint8 image u, and CLIP's preprocess
 // is (u/255 - mean_c)/std_c, so conv1 collapses to K = 256:
 //   W_eff[o][k] = sum_c W[o][c][k] / (255 std_c),   b_eff[o] = -sum_c mean_c/std_c sum_k W[o][c][k]
-__global__ void fold_patch_kernel(const float *__restrict__ conv1, __nv_bfloat16 *__restrict__ w_eff,
+__global__ void fold_patch_kernel(const float *__restrict__ conv1, op_t *__restrict__ w_eff,
                                   float *__restrict__ b_eff)
 {
     const double mean[3] = {0.48145466, 0.4578275, 0.40821073};
@@ -283,7 +279,7 @@ __global__ void fold_patch_kernel(const float *__restrict__ conv1, __nv_bfloat16
         wsum += wv / (255.0 * (double)(float)stdv[c]);
         bsum -= wv * ((double)(float)mean[c] / (double)(float)stdv[c]);
     }
-    w_eff[(size_t)o * 256 + k] = __float2bfloat16_rn((float)wsum);
+    w_eff[(size_t)o * 256 + k] = to_op((float)wsum);
     red[k] = bsum;
     __syncthreads();
     for (int s = 128; s; s >>= 1) {
@@ -298,7 +294,7 @@ __global__ void fold_patch_kernel(const float *__restrict__ conv1, __nv_bfloat16
 // scale_n = `scale` for n < scaled_rows (the 1/sqrt(64) query scale), 1 otherwise.
 __global__ void fold_ln_kernel(const float *__restrict__ W, const float *__restrict__ bias,
                                const float *__restrict__ gamma, const float *__restrict__ beta,
-                               int K, int scaled_rows, float scale, __nv_bfloat16 *__restrict__ Wf,
+                               int K, int scaled_rows, float scale, op_t *__restrict__ Wf,
                                float *__restrict__ colsum, float *__restrict__ cvec)
 {
     const int n = blockIdx.x, t = threadIdx.x;
@@ -307,9 +303,9 @@ __global__ void fold_ln_kernel(const float *__restrict__ W, const float *__restr
     double s = 0.0, c = 0.0;
     for (int k = t; k < K; k += 256) {
         const float wv = W[(size_t)n * K + k];
-        const __nv_bfloat16 wf = __float2bfloat16_rn(sc * gamma[k] * wv);
+        const op_t wf = to_op(sc * gamma[k] * wv);
         Wf[(size_t)n * K + k] = wf;
-        s += (double)__bfloat162float(wf);
+        s += (double)from_op(wf);
         c += (double)beta[k] * (double)wv;
     }
     red[0][t] = s; red[1][t] = c;
@@ -333,7 +329,7 @@ __global__ void patch_table_kernel(const float *__restrict__ cls, const float *_
 }  // namespace
 
 int launch_layernorm_bf16(VgHandle *h, const float *x, const float *w, const float *b, int64_t rows,
-                          __nv_bfloat16 *y, cudaStream_t st)
+                          op_t *y, cudaStream_t st)
 {
     if (rows <= 0) return VG_OK;
     VgProfScope prof(h, VG_K_LAYERNORM, (double)rows * kWidth * 6.0, st);
@@ -342,7 +338,7 @@ int launch_layernorm_bf16(VgHandle *h, const float *x, const float *w, const flo
     return VG_OK;
 }
 
-int launch_ln_pre(VgHandle *h, float *x, int64_t B, __nv_bfloat16 *xb, float *stats, cudaStream_t st)
+int launch_ln_pre(VgHandle *h, float *x, int64_t B, op_t *xb, float *stats, cudaStream_t st)
 {
     const int64_t rows = B * kTokens;
     if (rows <= 0) return VG_OK;
@@ -402,7 +398,7 @@ int convert_weights(VgHandle *h, const VgVitWeights *w, cudaStream_t st)
     h->arena_bytes = bytes;
     char *A = static_cast<char *>(h->arena);
     VitDev &d = h->vit;
-    d.w_patch = reinterpret_cast<__nv_bfloat16 *>(A + o_wpatch);
+    d.w_patch = reinterpret_cast<op_t *>(A + o_wpatch);
     float *b_eff = reinterpret_cast<float *>(A + o_beff);
     d.patch_bias_pos = reinterpret_cast<float *>(A + o_table);
     d.ln_pre_w = reinterpret_cast<float *>(A + o_lnpre);
@@ -411,7 +407,7 @@ int convert_weights(VgHandle *h, const VgVitWeights *w, cudaStream_t st)
     d.ln_post_b = d.ln_post_w + kWidth;
     d.proj = reinterpret_cast<float *>(A + o_proj);
 
-    auto cvt = [&](const float *src, __nv_bfloat16 *dst, size_t n, size_t pref, float sc) {
+    auto cvt = [&](const float *src, op_t *dst, size_t n, size_t pref, float sc) {
         f32_to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst, n, pref, sc);
         h->launches++;
     };
@@ -431,10 +427,10 @@ int convert_weights(VgHandle *h, const VgVitWeights *w, cudaStream_t st)
         const VgVitLayerWeights &s = w->layers[l];
         LayerDev &t = d.layer[l];
         char *p = A + o_layer[l];
-        t.w_qkv = reinterpret_cast<__nv_bfloat16 *>(p); p += n_qkv * 2;
-        t.w_out = reinterpret_cast<__nv_bfloat16 *>(p); p += n_out * 2;
-        t.w_fc = reinterpret_cast<__nv_bfloat16 *>(p); p += n_fc * 2;
-        t.w_proj = reinterpret_cast<__nv_bfloat16 *>(p); p += n_fc * 2;
+        t.w_qkv = reinterpret_cast<op_t *>(p); p += n_qkv * 2;
+        t.w_out = reinterpret_cast<op_t *>(p); p += n_out * 2;
+        t.w_fc = reinterpret_cast<op_t *>(p); p += n_fc * 2;
+        t.w_proj = reinterpret_cast<op_t *>(p); p += n_fc * 2;
         float *f = reinterpret_cast<float *>(p);
         t.b_qkv = f; f += 3 * kWidth;
         t.b_out = f; f += kWidth;
@@ -448,7 +444,7 @@ int convert_weights(VgHandle *h, const VgVitWeights *w, cudaStream_t st)
         t.c_qkv = f; f += 3 * kWidth;
         t.s_fc = f; f += kMlp;
         t.c_fc = f; f += kMlp;
-        t.wf_qkv = reinterpret_cast<__nv_bfloat16 *>(f);
+        t.wf_qkv = reinterpret_cast<op_t *>(f);
         t.wf_fc = t.wf_qkv + n_qkv;
         // 1/sqrt(head_dim) = 0.125 folded into the q rows (exact: power of two)
         cvt(s.attn_in_proj_weight, t.w_qkv, n_qkv, (size_t)kWidth * kWidth, 0.125f);

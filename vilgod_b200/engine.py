@@ -59,10 +59,12 @@ class Engine:
     def __init__(self, num_views: int = 4, rot_mat=None, resolution: int = 112, depth: int = 8,
                  image_size: int = 224, obj_ratio: float = 0.8, depth_bias: float = 0.2,
                  gauss=None, logit_scale: float = 100.0, rotate_mode: int = _lib.VG_ROTATE_TORCH_CPU,
-                 device=None):
+                 device=None, operand_dtype: str = "bf16"):
         if not torch.cuda.is_available():
             raise RuntimeError("vilgod_b200 needs an sm_100 CUDA device; there is no CPU fallback")
-        self.lib = _lib.load()
+        self.lib = _lib.load(operand_dtype)
+        self.operand_dtype = operand_dtype
+        self.op_torch_dtype = torch.float16 if operand_dtype == "f16" else torch.bfloat16
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
             else torch.device(device)
         rot = views.view_rot_mats(num_views) if rot_mat is None else torch.as_tensor(rot_mat).float()
@@ -185,7 +187,7 @@ class Engine:
         p, o, Cn = self._packed(points, offsets)
         B, R, S = Cn * self.num_views, self.resolution, self.image_size
         out = {}
-        tiles = torch.empty((B, 196, 256), dtype=torch.bfloat16, device=self.device) if want_tiles else None
+        tiles = torch.empty((B, 196, 256), dtype=self.op_torch_dtype, device=self.device) if want_tiles else None
         u8 = torch.empty((B, S, S), dtype=torch.uint8, device=self.device) if want_u8 else None
         status = torch.empty((Cn,), dtype=torch.int32, device=self.device)
         dbg = _lib.VgProjectDebug()
@@ -203,8 +205,8 @@ class Engine:
                      stop_after_layer: Optional[int] = None):
         """bf16 tiles [B,196,256] -> dict(probs [B,P], top1 [B], feats [B,512], logits [B,P]).
         ``stop_after_layer`` (-2: after ln_pre, k: after resblock k) returns only 'x' [B,197,768]."""
-        if tiles.dtype != torch.bfloat16 or tiles.ndim != 3 or tiles.shape[1:] != (196, 256):
-            raise ValueError("tiles must be bf16 [B,196,256]")
+        if tiles.dtype != self.op_torch_dtype or tiles.ndim != 3 or tiles.shape[1:] != (196, 256):
+            raise ValueError(f"tiles must be {self.op_torch_dtype} [B,196,256]")
         tiles = tiles.to(self.device).contiguous()
         B, P = tiles.shape[0], self.num_prompts
         ws = self.workspace(B)
@@ -276,7 +278,7 @@ class Engine:
         N = w.shape[0]
         if out is None:
             out = torch.empty((M, N), device=self.device,
-                              dtype=torch.float32 if epilogue == _lib.VG_EPI_BIAS_RESID_F32 else torch.bfloat16)
+                              dtype=torch.float32 if epilogue == _lib.VG_EPI_BIAS_RESID_F32 else self.op_torch_dtype)
         with torch.cuda.device(self.device):
             self._check(self.lib.vg_test_gemm(self._h, _ptr(a), _ptr(w), _ptr(bias), M, N, K,
                                               epilogue, _ptr(out), _stream()))
@@ -284,22 +286,22 @@ class Engine:
 
     def test_attention(self, qkv):
         B = qkv.shape[0]
-        out = torch.empty((B, 197, 768), dtype=torch.bfloat16, device=self.device)
+        out = torch.empty((B, 197, 768), dtype=self.op_torch_dtype, device=self.device)
         with torch.cuda.device(self.device):
             self._check(self.lib.vg_test_attention(self._h, _ptr(qkv), B, _ptr(out), _stream()))
         return out
 
     def test_layernorm(self, x, w, b):
-        y = torch.empty(x.shape, dtype=torch.bfloat16, device=self.device)
+        y = torch.empty(x.shape, dtype=self.op_torch_dtype, device=self.device)
         with torch.cuda.device(self.device):
             self._check(self.lib.vg_test_layernorm(self._h, _ptr(x), _ptr(w), _ptr(b),
                                                    x.shape[0], _ptr(y), _stream()))
         return y
 
 
-def u8_to_tiles(u8: torch.Tensor) -> torch.Tensor:
-    """uint8 [B,224,224] -> patch-major bf16 tiles [B,196,256] (layout plumbing for callers that
-    already hold images, e.g. ClipWrapper.predict_clip_labels)."""
+def u8_to_tiles(u8: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
+    """uint8 [B,224,224] -> patch-major tiles [B,196,256] in the engine's operand dtype (layout
+    plumbing for callers that already hold images, e.g. ClipWrapper.predict_clip_labels)."""
     B = u8.shape[0]
     t = u8.reshape(B, 14, 16, 14, 16).permute(0, 1, 3, 2, 4).reshape(B, 196, 256)
-    return t.to(torch.bfloat16).contiguous()
+    return t.to(dtype).contiguous()

@@ -126,7 +126,7 @@ class ClipWrapper:
         if arr.shape[1:] != (224, 224) or arr.dtype != np.uint8:
             raise ValueError("expected uint8 224x224 images")
         u8 = torch.from_numpy(np.ascontiguousarray(arr)).to(self.engine.device)
-        res = self.engine.encode_score(u8_to_tiles(u8), want_feats=False)
+        res = self.engine.encode_score(u8_to_tiles(u8, self.engine.op_torch_dtype), want_feats=False)
         probs = res["probs"].cpu().numpy()
         top1 = res["top1"].cpu().numpy()
         names = [self.id_to_class_dict[int(i)] for i in top1]
