@@ -9,6 +9,9 @@
  *   vg_load_vit_weights          clip.load / build_model        third_party/CLIP/clip/clip.py:94-142,
  *                                                               third_party/CLIP/clip/model.py:399-436
  *   vg_set_text_features         ClipWrapper.__init__           src/utils/clip_utils.py:21-26
+ *   vg_canonicalise              apply_transform +              src/utils/pointcloud_utils.py:21-46,
+ *                                transform_cluster_points_to_origin                         :390-412
+ *                                (call site src/vilgod/zero_shot_detector.py:391-394)
  *   vg_project                   RealisticProjection.get_img    src/utils/mv_utils.py:173-187
  *                                + upsample/uint8 glue          src/vilgod/zero_shot_detector.py:405-409
  *                                + CLIP preprocess (folded)     third_party/CLIP/clip/clip.py:79-86
@@ -136,6 +139,15 @@ VG_API int vg_set_text_features(VgHandle *h, const float *d_text, int32_t P, con
 
 /* bytes of scratch vg_encode_score / vg_classify need for up to max_images images per call */
 VG_API size_t vg_workspace_bytes(const VgHandle *h, int64_t max_images);
+
+/* Cluster canonicalisation for a packed frame: ego transform (nullable: d_transform = 16 doubles,
+ * row-major 4x4, device memory), subtract the xy median, rotate the median direction onto the view
+ * ray, shift, reorder to image axes.  d_points_in / d_points_out: [sum N, 3] fp32 (may not alias).
+ * fp32 medians are bit-identical to numpy's; the float64 chain matches the host path to <= 1 ulp of
+ * the fp32 result.  d_status [C] (nullable): VG_EDEGENERATE for empty clusters. */
+VG_API int vg_canonicalise(VgHandle *h, const float *d_points_in, const int32_t *d_offsets, int32_t C,
+                           const double *d_transform, float *d_points_out, int32_t *d_status,
+                           void *stream);
 
 /* Projection: packed ragged clusters -> B = C*V images, cluster-major / view-minor.
  *   d_points  [sum N, 3] fp32 (already canonicalised, zero_shot_detector.py:391-393)

@@ -78,6 +78,8 @@ SYMBOLS = {
     "vg_set_text_features": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32),
                                        C.c_int32, C.c_void_p]),
     "vg_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64]),
+    "vg_canonicalise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]),
     "vg_project": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                              C.c_void_p, C.POINTER(VgProjectDebug), C.c_void_p]),
     "vg_encode_score": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,

@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(OUT_DIR, "libvilgod_b200.so")           # bf16 GEMM operands (default)
 LIB_PATH_F16 = os.path.join(OUT_DIR, "libvilgod_b200_f16.so")   # fp16 GEMM operands (-DVG_OPERAND_F16)
-SOURCES = ["api.cu", "projection.cu", "gemm_tcgen05.cu", "gemm_tcgen05_2cta.cu", "attention.cu",
+SOURCES = ["api.cu", "canonicalise.cu", "projection.cu", "gemm_tcgen05.cu", "gemm_tcgen05_2cta.cu", "attention.cu",
            "attention_tcgen05.cu",
            "vit_misc.cu"]
 HEADERS = ["common.cuh", "ptx.cuh", os.path.join("..", "..", "include", "vilgod_b200.h")]

@@ -250,6 +250,19 @@ size_t vg_workspace_bytes(const VgHandle *h, int64_t max_images)
     return encode_bytes(chunk) + align_up((size_t)chunk * kTileBytesPerImage, 1024) + 4096;
 }
 
+int vg_canonicalise(VgHandle *h, const float *d_points_in, const int32_t *d_offsets, int32_t C,
+                    const double *d_transform, float *d_points_out, int32_t *d_status, void *stream)
+{
+    if (!h) return VG_EINVAL;
+    if (C < 0 || (C > 0 && (!d_points_in || !d_offsets || !d_points_out)) ||
+        (C > 0 && d_points_in == d_points_out)) {
+        VG_SET_ERR(h, "vg_canonicalise: null / aliasing buffers or negative cluster count");
+        return VG_EINVAL;
+    }
+    return launch_canonicalise(h, d_points_in, d_offsets, C, d_transform, d_points_out, d_status,
+                               static_cast<cudaStream_t>(stream));
+}
+
 int vg_project(VgHandle *h, const float *d_points, const int32_t *d_offsets, int32_t C,
                void *d_tiles, uint8_t *d_u8, int32_t *d_status, const VgProjectDebug *dbg,
                void *stream)

@@ -151,6 +151,8 @@ struct VgProfScope {
 // kernel launchers implemented in the .cu files ------------------------------------------------
 namespace vg {
 
+int launch_canonicalise(VgHandle *h, const float *d_in, const int32_t *d_offsets, int32_t C,
+                        const double *d_transform, float *d_out, int32_t *d_status, cudaStream_t st);
 int projection_init(VgHandle *h);   // builds the handle-owned projection tables (vg_create)
 int launch_projection(VgHandle *h, const float *d_points, const int32_t *d_offsets, int32_t C,
                       op_t *d_tiles, uint8_t *d_u8, int32_t *d_status,

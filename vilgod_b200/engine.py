@@ -180,6 +180,22 @@ class Engine:
             raise ValueError("points must be [sum N, 3] and offsets [C+1]")
         return p, o, o.numel() - 1
 
+    def canonicalise(self, points_raw, offsets, transform_to_ego=None):
+        """GPU version of ``canonicalise.canonicalise_packed``: raw fp32 cluster points [sum N,3] (+ the
+        frame's 4x4 ego transform) -> canonicalised fp32 points on the device."""
+        p, o, Cn = self._packed(points_raw, offsets)
+        out = torch.empty_like(p)
+        status = torch.empty((Cn,), dtype=torch.int32, device=self.device)
+        T = None
+        if transform_to_ego is not None:
+            T = torch.as_tensor(np.asarray(transform_to_ego, dtype=np.float64)).to(self.device).contiguous()
+            if T.shape != (4, 4):
+                raise ValueError("transform_to_ego must be 4x4")
+        with torch.cuda.device(self.device):
+            self._check(self.lib.vg_canonicalise(self._h, _ptr(p), _ptr(o), Cn, _ptr(T), _ptr(out),
+                                                 _ptr(status), _stream()))
+        return out, status
+
     def project(self, points, offsets, want_tiles=True, want_u8=False, want_grid=False,
                 want_densified=False):
         """Packed clusters -> dict with 'tiles' bf16 [B,196,256], 'u8' [B,224,224], 'status' [C],

@@ -134,7 +134,7 @@ class ClipWrapper:
         return names, scores
 
 
-def classify_frame(engine: Engine, clusters, transform_to_ego=None, key=None):
+def classify_frame(engine: Engine, clusters, transform_to_ego=None, key=None, gpu_canonicalise=False):
     """One frame of ZeroShotDetector.classification on the GPU.
 
     clusters: list of [N_i, >=3] arrays (``det.cluster_points``) in the reference frame.
@@ -144,7 +144,10 @@ def classify_frame(engine: Engine, clusters, transform_to_ego=None, key=None):
     pts = [np.asarray(c)[..., :3] for c in clusters]
     offsets = np.zeros(len(pts) + 1, dtype=np.int32)
     offsets[1:] = np.cumsum([len(p) for p in pts])
-    packed = canonicalise.canonicalise_packed(np.concatenate(pts), offsets, transform_to_ego)
+    if gpu_canonicalise:     # no host loop at all (fp32 cluster points expected)
+        packed, _ = engine.canonicalise(np.concatenate(pts).astype(np.float32), offsets, transform_to_ego)
+    else:
+        packed = canonicalise.canonicalise_packed(np.concatenate(pts), offsets, transform_to_ego)
     out = engine.classify(packed, offsets, want_feats=False)
     top1 = out["top1"].cpu().numpy()
     probs = out["probs"].cpu().numpy()
