@@ -48,7 +48,7 @@ template <int EPI, bool LNF> struct EpiCfg {
     static constexpr int kWarps = kResid ? 4 : 8;
     static constexpr int kSlabs = kResid ? (LNF ? 6 : 4) : 2;   // f32: 2 in + 2 out (+ 2 bf16 out)
     static constexpr int kThreads = 64 + 32 * kWarps;
-    static constexpr int kStages = 4;
+    static constexpr int kStages = kResid ? 4 : 5;   // bf16 epilogues have 32 KiB to spare: one more stage
     static constexpr int kEpiBytes = kWarps * kSlabs * SLAB_BYTES;          // 64 KiB / 96 KiB
     static constexpr size_t kSmem = (size_t)kStages * STAGE_BYTES + kEpiBytes + 1024 + 512;
 };
