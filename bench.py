@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--clusters-per-frame", type=int, default=300)
     ap.add_argument("--views", type=int, default=10)
     ap.add_argument("--n-max", type=int, default=2048)
-    ap.add_argument("--cpu-sample-clusters", type=int, default=16)
+    ap.add_argument("--cpu-sample-clusters", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=20240807)
     ap.add_argument("--operand-dtype", default="bf16", choices=["bf16", "f16"],
@@ -318,7 +318,7 @@ def run_ours(a):
         all_ms = sum(v["ms"] for v in prof.values())
         gemm_tflops = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         roofline = {"bound": "tensor", "kernel": "gemm2_kernel<EPI,LNF> (2-CTA tcgen05; QKV / out-proj / c_fc / c_proj) + gemm_kernel<patch>",
