@@ -211,13 +211,10 @@ int launch_attention(VgHandle *h, const op_t *qkv_op, int64_t B, op_t *out_op,
     if (!force_v1) return launch_attention_tc(h, qkv_op, B, out_op, st);
     const __nv_bfloat16 *qkv = reinterpret_cast<const __nv_bfloat16 *>(qkv_op);
     __nv_bfloat16 *out = reinterpret_cast<__nv_bfloat16 *>(out_op);
-    static bool attr_set = false;
-    if (!attr_set) {
-        VG_CUDA_CHECK(h, cudaFuncSetAttribute(attention_kernel,
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)ATT_SMEM));
-        attr_set = true;
-    }
+    // per device and cheap: set on every launch rather than caching in process-wide state
+    VG_CUDA_CHECK(h, cudaFuncSetAttribute(attention_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)ATT_SMEM));
     VgProfScope prof(h, VG_K_ATTENTION, 4.0 * (double)B * kHeads * L * L * HD, st);
     attention_kernel<<<(unsigned)(B * kHeads), ATT_THREADS, ATT_SMEM, st>>>(qkv, out);
     VG_LAUNCH_CHECK(h);

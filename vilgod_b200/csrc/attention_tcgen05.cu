@@ -414,13 +414,10 @@ int launch_attention_tc(VgHandle *h, const op_t *qkv, int64_t B, op_t *out,
         VG_SET_ERR(h, "attention: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
         return VG_ECUDA;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        VG_CUDA_CHECK(h, cudaFuncSetAttribute(attention_tc_kernel,
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)SMEM_BYTES));
-        attr_set = true;
-    }
+    // per device and cheap: set on every launch rather than caching in process-wide state
+    VG_CUDA_CHECK(h, cudaFuncSetAttribute(attention_tc_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)SMEM_BYTES));
     const int64_t items = B * kHeads;
     const int grid = (int)(items < h->num_sms ? items : h->num_sms);
     VgProfScope prof(h, VG_K_ATTENTION, 4.0 * (double)B * kHeads * L * L * HD, st);

@@ -254,13 +254,10 @@ int launch_gemm_t(VgHandle *h, const GemmArgs &g, cudaStream_t st)
     if (rc) return rc;
     rc = make_tmap_2d(h, &tb, g.w, (uint64_t)g.N, (uint64_t)g.K, BN, BK);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        VG_CUDA_CHECK(h, cudaFuncSetAttribute(gemm_kernel<EPI>,
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)GEMM_SMEM));
-        attr_set = true;
-    }
+    // per device and cheap: set on every launch rather than caching in process-wide state
+    VG_CUDA_CHECK(h, cudaFuncSetAttribute(gemm_kernel<EPI>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)GEMM_SMEM));
     GemmParams p;
     p.bias = g.bias;
     p.out = g.out;
