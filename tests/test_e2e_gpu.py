@@ -131,3 +131,48 @@ def test_classify_frame_mirror_and_chunking(golden, engine6):
         e._ws = None
     assert torch.equal(small["probs"], probs_full)
     assert torch.equal(small["voted_class"], full["voted_class"])
+
+
+def test_classify_is_cuda_graph_capturable(golden, engine6):
+    """no hidden allocation or synchronisation after the weights are loaded,
+    so one frame of vg_classify can be captured once and replayed on new points (same shapes)."""
+    from vilgod_b200 import canonicalise, synthetic
+    e = engine6
+    e.set_text_features(golden["tables"]["text_features"])
+    raw, off, _ = synthetic.make_clusters_raw(16, n_min=10, n_max=400, seed=21)
+    packed = canonicalise.canonicalise_packed(raw, off, np.eye(4))
+    p_static = torch.as_tensor(packed, dtype=torch.float32).cuda()
+    o_static = torch.as_tensor(off, dtype=torch.int32).cuda()
+    eager = e.classify(p_static, o_static)
+    torch.cuda.synchronize()
+    eager = {k: v.clone() for k, v in eager.items() if v is not None}
+    out = e.alloc_outputs(16)
+    e.workspace(16 * 6)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        e.classify(p_static, o_static, out=out)          # warm-up on the capture stream
+    torch.cuda.current_stream().wait_stream(side)
+    launches0 = e.launch_count
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        e.classify(p_static, o_static, out=out)
+    captured = e.launch_count - launches0
+    assert captured > 0
+    for k in out:
+        if out[k] is not None:
+            out[k].zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert e.launch_count - launches0 == captured          # replay goes through no library call
+    for k, v in eager.items():
+        assert torch.equal(out[k], v), k
+    # replay on new points of the same packed shape: a permutation of the points inside each cluster
+    # leaves every result unchanged (scatter-max is order independent) but exercises fresh inputs
+    perm = np.concatenate([off[c] + np.random.default_rng(c).permutation(off[c + 1] - off[c])
+                           for c in range(16)])
+    p_static.copy_(torch.as_tensor(packed[perm], dtype=torch.float32))
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out["top1"], eager["top1"])
+    assert torch.equal(out["probs"], eager["probs"])

@@ -101,6 +101,31 @@ def test_bit_exact_against_oracle_all_stages(engines, V):
     assert torch.equal(tiles_to_u8(out["tiles"]), out["u8"])
 
 
+def test_large_clusters_reuse_the_spill_grids(engines):
+    """Clusters above the shared-memory point cache (1408) keep their remaining quantised points in
+    per-CTA global pools that are handed from CTA to CTA: more large images than pools, mixed with
+    small ones, twice in a row, must still equal the oracle bit for bit."""
+    from vilgod_b200 import synthetic
+    rng = np.random.default_rng(23)
+    parts, offs = [], [np.zeros(1, np.int64)]
+    for k in range(12):
+        big, boff = synthetic.make_clusters(6, n_min=1409, n_max=9000, rng=rng)
+        small, soff = synthetic.make_clusters(3, n_min=10, n_max=1408, rng=rng)
+        for p_, o_ in ((big, boff), (small, soff)):
+            parts.append(p_)
+            offs.append(o_[1:].astype(np.int64) + offs[-1][-1])
+    pts = np.concatenate(parts)
+    off = np.concatenate(offs).astype(np.int32)
+    eng = engines(6)                      # 72 large clusters x 6 views = 432 images > 296 pools
+    a = eng.project(pts, off, want_u8=True, want_densified=True)
+    b = eng.project(pts, off, want_u8=True)
+    assert torch.equal(a["u8"], b["u8"]) and torch.equal(a["tiles"], b["tiles"])
+    dens_o, u8_o = opipe.project(pts, off, 6, want_dens=True)
+    assert np.array_equal(a["densified"].cpu().numpy().reshape(dens_o.shape), dens_o)
+    assert np.array_equal(a["u8"].cpu().numpy().reshape(u8_o.shape), u8_o)
+    assert int(a["status"].abs().sum()) == 0
+
+
 def test_rotation_modes(engines):
     from vilgod_b200 import _lib, synthetic
     pts, off = synthetic.make_clusters(12, n_min=10, n_max=80, seed=3)

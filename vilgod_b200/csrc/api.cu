@@ -163,6 +163,8 @@ void vg_destroy(VgHandle *h)
     if (!h) return;
     if (h->arena) cudaFree(h->arena);
     if (h->proj_tables) cudaFree(h->proj_tables);
+    if (h->proj_spill) cudaFree(h->proj_spill);
+    if (h->proj_spill_flags) cudaFree(h->proj_spill_flags);
     if (h->d_text) cudaFree(h->d_text);
     if (h->d_class_map) cudaFree(h->d_class_map);
     for (auto &r : h->prof) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }

@@ -98,6 +98,9 @@ struct VgHandle {
     size_t arena_bytes = 0;
     void *tma_encode = nullptr;     // cuTensorMapEncodeTiled entry point
     void *proj_tables = nullptr;    // bilinear tables + background tile (projection.cu)
+    void *proj_spill = nullptr;     // per-resident-CTA global depth grids for clusters > CAP points
+    void *proj_spill_flags = nullptr;
+    int proj_spill_sms = 0;
 };
 
 #define VG_SET_ERR(h, ...)                                   \

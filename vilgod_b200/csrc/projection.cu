@@ -34,11 +34,15 @@ constexpr int NT = 512;         // threads per CTA
 constexpr int NW = NT / 32;     // 16 warps
 constexpr int CH = 7;           // rows per warp chunk in the stencil passes (16 x 7 = 112)
 constexpr int HI_ROWS = 56;     // source rows whose horizontal interpolation fits the grid buffer
+constexpr int POOL = 65536 - 1408;   // pooled points per resident CTA (N <= 65,536 never recomputes)
+constexpr int kSpillPerSm = 2;  // resident CTAs per SM (shared memory bound)
 constexpr int CAP = 1408;       // points whose quantised (cell, slice, value) are cached in smem
 
 // bilinear index / weight table (identical for rows and columns: square images) and the image a
 // cluster-free region produces, both built once per handle by projection_tables_kernel
 struct ProjTables {
+    int nsmid;             // upper bound of %smid on this device
+    int pad_[3];
     int i0[S];
     float l0[S], l1[S];
     uint4 bg_tile[VG_TILE_ELEMS * 2 / 16];
@@ -49,6 +53,9 @@ struct ProjParams {
     const float *points;
     const int32_t *offsets;
     const ProjTables *tab;
+    uint2 *spill;          // [slots][POOL] quantised points beyond the shared-memory cache
+    int *spill_flags;      // [slots] 0 = free
+    int32_t spill_sms;     // SM ids covered by the spill pool (%nsmid)
     int32_t C, V;
     float rot[VG_MAX_VIEWS * 9];
     float gauss[9];
@@ -73,6 +80,7 @@ struct Smem {
     int ulo, uhi;          // rows of IMG any slice can touch
     unsigned mask;         // occupied depth slices
     int degenerate;
+    int spill_slot;        // global point pool of this CTA (clusters above CAP points), -1 = none
 };
 
 using f32x2 = unsigned long long;   // two packed fp32 (FFMA2 / FMUL2 / FADD2 on sm_100)
@@ -206,6 +214,11 @@ __device__ __forceinline__ float quant255(float o)
 __global__ void projection_tables_kernel(ProjTables *t)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid == 0) {
+        unsigned nsm;
+        asm volatile("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+        t->nsmid = (int)nsm;
+    }
     if (tid < S) {
         int i0; float l0, l1;
         lin_idx(tid, i0, l0, l1);
@@ -301,6 +314,24 @@ __global__ void __launch_bounds__(NT, 2) projection_kernel(const ProjParams P)
     qn.slow = !(qn.pr > 1e-18f && qn.pr < 1e18f);
 
     // ---- phase 2: quantise once; occupied slices and rows; cache (cell, slice, value) ------------
+    // The first CAP points keep their quantised (cell, slice, value) in shared memory and are replayed
+    // per slice.  Points beyond that go to a private pool in global memory (L2 resident; one per
+    // resident CTA, claimed per SM), so no point is rotated and quantised more than once per view.
+    const bool big = n > CAP;
+    if (big && tid == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        int slot = -1;
+        for (int k = 0; k < kSpillPerSm && slot < 0 && (int)smid < P.spill_sms; ++k)
+            if (atomicCAS(&P.spill_flags[smid * kSpillPerSm + k], 0, 1) == 0)
+                slot = (int)smid * kSpillPerSm + k;
+        __threadfence();
+        sm.spill_slot = slot;
+    }
+    if (big) __syncthreads();
+    uint2 *pool = nullptr;
+    if (big && sm.spill_slot >= 0) pool = P.spill + (size_t)sm.spill_slot * POOL;
+    const int npool = pool ? min(n - CAP, POOL) : 0;
     {
         unsigned m = 0u;
         for (int i = tid; i < n; i += NT) {
@@ -309,8 +340,9 @@ __global__ void __launch_bounds__(NT, 2) projection_kernel(const ProjParams P)
             quantise(qx, qy, qz, qn, P, X, Y, zi, val);
             m |= 1u << zi;
             atomicOr(&sm.rowmask[zi][Y >> 5], 1u << (Y & 31));
-            if (i < CAP) sm.cache[i] = make_uint2((unsigned)(Y * R + X) | ((unsigned)zi << 16),
-                                                  __float_as_uint(val));
+            const uint2 e = make_uint2((unsigned)(Y * R + X) | ((unsigned)zi << 16), __float_as_uint(val));
+            if (i < CAP) sm.cache[i] = e;
+            else if (i - CAP < npool) __stcg(pool + (i - CAP), e);
         }
         m = __reduce_or_sync(0xffffffffu, m);
         if (lane == 0 && m) atomicOr(&sm.mask, m);
@@ -375,7 +407,20 @@ __global__ void __launch_bounds__(NT, 2) projection_kernel(const ProjParams P)
                 if ((int)(e.x >> 16) == d)
                     atomicMax(reinterpret_cast<int *>(sm.G) + (e.x & 0xffffu), (int)e.y);
             }
-            for (int i = CAP + tid; i < n; i += NT) {
+            // pooled points: 4 independent L2 loads in flight per thread
+            for (int i0 = tid; i0 < npool; i0 += 4 * NT) {
+                uint2 e[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    e[k] = i0 + k * NT < npool ? __ldcg(pool + i0 + k * NT) : make_uint2(0xffffffffu, 0u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if ((int)(e[k].x >> 16) == d)
+                        atomicMax(reinterpret_cast<int *>(sm.G) + (e[k].x & 0xffffu), (int)e[k].y);
+            }
+            // beyond the pool (N > CAP + POOL), or every pool of this SM taken (cannot happen at two
+            // resident CTAs per SM): rotate and quantise again
+            for (int i = CAP + npool + tid; i < n; i += NT) {
                 float qx, qy, qz, val; int X, Y, zi;
                 rotate_point(pts + 3 * i, rm, fused, qx, qy, qz);
                 quantise(qx, qy, qz, qn, P, X, Y, zi, val);
@@ -495,6 +540,14 @@ __global__ void __launch_bounds__(NT, 2) projection_kernel(const ProjParams P)
             }
         }
         __syncthreads();
+    }
+
+    if (big) {   // hand the pool back (every read of it is behind the last slice's barriers)
+        __syncthreads();
+        if (tid == 0 && sm.spill_slot >= 0) {
+            __threadfence();
+            atomicExch(&P.spill_flags[sm.spill_slot], 0);
+        }
     }
 
     // ---- phase 4: img / max(img), 1 - x  (rows the emit reads; everything else is background) ----
@@ -639,6 +692,16 @@ int projection_init(VgHandle *h)
                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)sizeof(Smem)));
     h->proj_tables = t;
+    // point pools for clusters above CAP points: one per CTA that can be resident (~150 MB)
+    int nsmid = 0;
+    VG_CUDA_CHECK(h, cudaMemcpy(&nsmid, &t->nsmid, sizeof(int), cudaMemcpyDeviceToHost));
+    if (nsmid < h->num_sms) nsmid = h->num_sms;
+    h->proj_spill_sms = nsmid;
+    const size_t slots = (size_t)nsmid * kSpillPerSm;
+    VG_CUDA_CHECK(h, cudaMalloc(&h->proj_spill, slots * POOL * sizeof(uint2)));
+    VG_CUDA_CHECK(h, cudaMalloc(&h->proj_spill_flags, slots * sizeof(int)));
+    VG_CUDA_CHECK(h, cudaMemset(h->proj_spill_flags, 0, slots * sizeof(int)));
+    VG_CUDA_CHECK(h, cudaDeviceSynchronize());
     return VG_OK;
 }
 
@@ -657,6 +720,9 @@ int launch_projection(VgHandle *h, const float *d_points, const int32_t *d_offse
     P.points = d_points;
     P.offsets = d_offsets;
     P.tab = static_cast<const ProjTables *>(h->proj_tables);
+    P.spill = static_cast<uint2 *>(h->proj_spill);
+    P.spill_flags = static_cast<int *>(h->proj_spill_flags);
+    P.spill_sms = h->proj_spill_sms;
     P.C = C;
     P.V = cfg.num_views;
     memcpy(P.rot, cfg.rot, sizeof(P.rot));
