@@ -36,7 +36,10 @@ constexpr int KV_BYTES = LP * 128;            // 26,624
 constexpr int STAGE_BYTES = Q_BYTES + 2 * KV_BYTES;   // 86,016
 constexpr int BOX_BYTES = LP * 128;
 constexpr int STAGES = 2;
-constexpr int THREADS = 480;          // warps 0-7 soft-max, 8-11 epilogue, 12 TMA, 13-14 MMA (one per slot)
+constexpr int THREADS = 512;          // warps 0-7 soft-max, 8-11 epilogue, 12 TMA, 13-14 MMA (one per slot), 15 idle
+// Register file split by warpgroup (setmaxnreg): the soft-max warps keep a whole row half of S (up to
+// 112 fp32) in registers, the issuer warps need almost none.  176*2 + 104 + 56 = 512 = 4 * 128.
+constexpr int REGS_SOFTMAX = 176, REGS_EPILOGUE = 104, REGS_ISSUE = 56;
 // The warp scheduler favours the highest warp id of an SM sub-partition: the single-thread TMA and
 // MMA issuers get the top ids so that they are never starved by the MUFU-bound soft-max warps.
 constexpr int W_TMA = 12, W_MMA = 13, W_EPI0 = 8;
@@ -85,6 +88,14 @@ __device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&r)[8
         "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
         "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
         : "memory");
+}
+template <int N> __device__ __forceinline__ void reg_alloc()
+{
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N> __device__ __forceinline__ void reg_dealloc()
+{
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 __device__ __forceinline__ void tmem_st_wait()
 {
@@ -186,6 +197,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, op_t *__restric
     const uint32_t tmem_base = *tmem_slot;
     const int n_my = (int)((num_items - blockIdx.x + gridDim.x - 1) / gridDim.x);   // items of this CTA
 
+    if (warp >= W_TMA) reg_dealloc<REGS_ISSUE>();      // warpgroup 3: TMA, 2 x MMA, one idle warp
     if (warp == W_TMA) {
         // ================= TMA producer =================
         if (lane == 0) {
@@ -204,7 +216,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, op_t *__restric
                             img);                                                                  // V
             }
         }
-    } else if (warp >= W_MMA) {
+    } else if (warp == W_MMA || warp == W_MMA + 1) {
         // ================= MMA issuers: one warp per TMEM slot =================
         // Each runs convergently with blocking mbarrier waits (cheap wake-up); one elected lane issues
         // the tcgen05 instructions so descriptors and addresses stay in uniform registers.  The
@@ -254,6 +266,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, op_t *__restric
         }
     } else if (warp < W_EPI0) {
         // ================= soft-max warps: 8 warps on one unit at a time =================
+        reg_alloc<REGS_SOFTMAX>();
         const int quarter = warp & 3;                     // TMEM lane quarter of this warp
         const int half = warp >> 2;                       // which half of the keys this warp owns
         constexpr float kLog2e = 1.4426950408889634f;
@@ -270,62 +283,60 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, op_t *__restric
                 if (quarter == 0 && lane == 0 && half == 0) VG_TRACE(slot * 5 + 0, it);
                 ptx::tc_fence_after();
                 if (warp_has_rows) {
-                    // pass 1: maximum of this warp's keys (TMEM loads software-pipelined, 3-input max)
-                    float m = -INFINITY;
-                    uint32_t r[2][16];
-                    auto pass1 = [&](auto half_tag) {
+                    // The whole row half of S comes out of TMEM once (every tcgen05.wait::ld costs
+                    // ~100 cycles, so one wait per block instead of one per 16 columns and pass), is
+                    // reduced to its maximum, exchanged with the partner warp, and exponentiated
+                    // straight from registers.
+                    auto run = [&](auto half_tag) {
                         constexpr int c_lo = decltype(half_tag)::value ? HALF_CH : 0;
                         constexpr int c_hi = decltype(half_tag)::value ? LP / 16 : HALF_CH;
-                        tmem_ld_x16(t_slot + (uint32_t)(c_lo * 16), r[c_lo & 1]);
+                        constexpr int NC = c_hi - c_lo;
+                        uint32_t sv[NC][16];
 #pragma unroll
-                        for (int ch = c_lo; ch < c_hi; ++ch) {
-                            ptx::tmem_ld_wait();
-                            if (ch + 1 < c_hi) tmem_ld_x16(t_slot + (uint32_t)((ch + 1) * 16), r[(ch + 1) & 1]);
+                        for (int k = 0; k < NC; ++k) tmem_ld_x16(t_slot + (uint32_t)((c_lo + k) * 16), sv[k]);
+                        ptx::tmem_ld_wait();
+                        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+                        for (int k = 0; k < NC; ++k) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                const int c0 = ch * 16 + 2 * j;
-                                if (c0 + 1 < L) m = max3(m, __uint_as_float(r[ch & 1][2 * j]), __uint_as_float(r[ch & 1][2 * j + 1]));
-                                else if (c0 < L) m = fmaxf(m, __uint_as_float(r[ch & 1][2 * j]));
+                                const int c0 = (c_lo + k) * 16 + 2 * j;
+                                float &m = m4[j & 3];
+                                if (c0 + 1 < L) m = max3(m, __uint_as_float(sv[k][2 * j]), __uint_as_float(sv[k][2 * j + 1]));
+                                else if (c0 < L) m = fmaxf(m, __uint_as_float(sv[k][2 * j]));
                             }
                         }
-                    };
-                    if (half) pass1(std::true_type{}); else pass1(std::false_type{});
-                    // exchange the half maxima between the two warps of this lane quarter
-                    xmax[(blk * 2 + half) * 128 + rib] = m;
-                    asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-                    m = fmaxf(m, xmax[(blk * 2 + (half ^ 1)) * 128 + rib]);
-                    if (quarter == 0 && lane == 0 && half == 0) VG_TRACE(slot * 5 + 1, it);
-                    // pass 2: p = exp2(s*log2e - m*log2e) on packed pairs, partial row sum, P -> TMEM
-                    const float mb = m * kLog2e;
-                    const f32x2 kl2 = pack2(kLog2e, kLog2e), kmb = pack2(-mb, -mb);
-                    f32x2 sum2 = pack2(0.0f, 0.0f);
-                    auto pass2 = [&](auto half_tag) {
-                        constexpr int c_lo = decltype(half_tag)::value ? HALF_CH : 0;
-                        constexpr int c_hi = decltype(half_tag)::value ? LP / 16 : HALF_CH;
-                        tmem_ld_x16(t_slot + (uint32_t)(c_lo * 16), r[c_lo & 1]);
+                        float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+                        // exchange the half maxima between the two warps of this lane quarter
+                        xmax[(blk * 2 + half) * 128 + rib] = m;
+                        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+                        m = fmaxf(m, xmax[(blk * 2 + (half ^ 1)) * 128 + rib]);
+                        if (quarter == 0 && lane == 0 && half == 0) VG_TRACE(slot * 5 + 1, it);
+                        // p = exp2(s*log2e - m*log2e) on packed pairs, partial row sum, P -> TMEM
+                        const float mb = m * kLog2e;
+                        const f32x2 kl2 = pack2(kLog2e, kLog2e), kmb = pack2(-mb, -mb);
+                        f32x2 sum2 = pack2(0.0f, 0.0f);
 #pragma unroll
-                        for (int ch = c_lo; ch < c_hi; ++ch) {
-                            ptx::tmem_ld_wait();
-                            if (ch + 1 < c_hi) tmem_ld_x16(t_slot + (uint32_t)((ch + 1) * 16), r[(ch + 1) & 1]);
+                        for (int k = 0; k < NC; ++k) {
                             uint32_t pk[8];
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                const int c0 = ch * 16 + 2 * j;
+                                const int c0 = (c_lo + k) * 16 + 2 * j;
                                 if (c0 >= L) { pk[j] = 0u; continue; }
                                 float t0, t1;
-                                unpack2(fma2(pack2(__uint_as_float(r[ch & 1][2 * j]), __uint_as_float(r[ch & 1][2 * j + 1])), kl2, kmb), t0, t1);
+                                unpack2(fma2(pack2(__uint_as_float(sv[k][2 * j]), __uint_as_float(sv[k][2 * j + 1])), kl2, kmb), t0, t1);
                                 const float p0 = ex2_approx(t0);
                                 const float p1 = c0 + 1 < L ? ex2_approx(t1) : 0.0f;
                                 sum2 = add2(sum2, pack2(p0, p1));
                                 pk[j] = pack_op(p0, p1);
                             }
-                            tmem_st_x8(t_slot + (uint32_t)p_col(ch), pk);
+                            tmem_st_x8(t_slot + (uint32_t)p_col(c_lo + k), pk);
                         }
+                        float sum, sum_hi;
+                        unpack2(sum2, sum, sum_hi);
+                        rsum[(slot * 2 + half) * 128 + rib] = sum + sum_hi;
                     };
-                    if (half) pass2(std::true_type{}); else pass2(std::false_type{});
-                    float sum, sum_hi;
-                    unpack2(sum2, sum, sum_hi);
-                    rsum[(slot * 2 + half) * 128 + rib] = sum + sum_hi;
+                    if (half) run(std::true_type{}); else run(std::false_type{});
                     tmem_st_wait();
                 }
                 ptx::tc_fence_before();
@@ -333,8 +344,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, op_t *__restric
                 ptx::mbar_arrive(&p_full[slot]);      // release: publishes rsum to the epilogue warps
             }
         }
-    } else {
+    } else if (warp < W_TMA) {
         // ================= epilogue warps (one per TMEM lane quarter) =================
+        reg_dealloc<REGS_EPILOGUE>();
         const int quarter = warp & 3;
         int it = 0;
         for (int64_t item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
