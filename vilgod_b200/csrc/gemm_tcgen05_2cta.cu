@@ -20,6 +20,7 @@
 //              TMA-loaded into the slab one chunk ahead, so the epilogue issues no per-thread global
 //              loads or stores at all.
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -43,17 +44,19 @@ constexpr int SLAB_BYTES = 4096;              // 32 rows x 128 B, SWIZZLE_128B
 //   bf16 epilogues     : A is the RAW residual stream in bf16, W carries the LayerNorm gain, and the
 //                        normalisation is applied after the matmul:
 //                        y = rstd_i * (acc - mu_i * colsum_n) + c_n      (model.py:157-163,190-191)
-// XIN (residual epilogue only): fp32 residual slabs in flight per warp.  The K = 768 out-proj GEMM is
-// HBM bound (9 KB of residual traffic per row against 0.23 GFLOP per image-layer): it trades one
-// operand stage for 4-deep residual prefetch so that enough loads are in flight to cover HBM latency.
-template <int EPI, bool LNF, int XIN = 2> struct EpiCfg {
+// WIDE (residual epilogue only): the K = 768 out-proj GEMM moves 9 KB of residual traffic per row for
+// 0.23 GFLOP per image-layer, so its epilogue (not the tensor pipe) sets the pace: 8 epilogue warps,
+// two per TMEM lane quarter with half of the columns each, paid for with one operand stage.
+template <int EPI, bool LNF, bool WIDE = false> struct EpiCfg {
     static constexpr bool kResid = EPI == VG_EPI_BIAS_RESID_F32;
-    static constexpr int kWarps = kResid ? 4 : 8;
-    static constexpr int kSlabs = kResid ? XIN + 2 + (LNF ? 2 : 0) : 2;   // f32: in + 2 out (+ 2 bf16 out)
+    static constexpr int kWarps = kResid ? (WIDE ? 8 : 4) : 8;
+    // f32 residual: 2 in + 2 out (+ 2 bf16 out); WIDE: 2 in + 1 out + 1 bf16 out per warp
+    static constexpr int kSlabs = kResid ? (WIDE ? 4 : 2 + 2 + (LNF ? 2 : 0)) : 2;
     static constexpr int kThreads = 64 + 32 * kWarps;
-    static constexpr int kStages = kResid ? (XIN > 2 ? 3 : 4) : 5;   // bf16 epilogues: 32 KiB to spare
-    static constexpr int kEpiBytes = kWarps * kSlabs * SLAB_BYTES;          // 64 KiB / 96 KiB
-    static constexpr size_t kSmem = (size_t)kStages * STAGE_BYTES + kEpiBytes + 1024 + 512;
+    static constexpr int kStages = kResid ? (WIDE ? 3 : 4) : 5;   // bf16 epilogues: 32 KiB to spare
+    static constexpr int kEpiBytes = kWarps * kSlabs * SLAB_BYTES;          // 64 / 96 / 128 KiB
+    static constexpr int kXchgBytes = WIDE ? 4 * 32 * 2 * 4 : 0;           // row-statistics hand-off
+    static constexpr size_t kSmem = (size_t)kStages * STAGE_BYTES + kEpiBytes + 1024 + 512 + kXchgBytes;
 };
 
 struct Params {
@@ -75,13 +78,14 @@ __device__ __forceinline__ float quick_gelu(float v)
 // 16-byte chunk c of row r inside a 1024-byte-aligned SWIZZLE_128B slab
 __device__ __forceinline__ uint32_t slab_off(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
 
-template <int EPI, bool LNF, int XIN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<EPI, LNF, XIN>::kThreads, 1)
+template <int EPI, bool LNF, bool WIDE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<EPI, LNF, WIDE>::kThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
              const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_xb,
              const Params p)
 {
-    using Cfg = EpiCfg<EPI, LNF, XIN>;
+    using Cfg = EpiCfg<EPI, LNF, WIDE>;
+    constexpr int XIN = 2;       // fp32 residual slabs in flight per epilogue warp
     constexpr int STAGES = Cfg::kStages;
     constexpr int EPI_BYTES = Cfg::kEpiBytes;
     extern __shared__ unsigned char smem_raw[];
@@ -95,8 +99,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     uint64_t *tmem_empty = bars + 2 * STAGES + ACC_STAGES;   // [ACC]      (leader's are used)
     constexpr int EPI_WARPS = Cfg::kWarps;
     constexpr int SLABS_PER_WARP = Cfg::kSlabs;
-    uint64_t *xin_bar = bars + 2 * STAGES + 2 * ACC_STAGES;  // [4 warps][XIN] (fp32 residual path)
+    uint64_t *xin_bar = bars + 2 * STAGES + 2 * ACC_STAGES;  // [epilogue warps][XIN] (fp32 residual path)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(xin_bar + 16);
+    float *xstat = reinterpret_cast<float *>(epi_smem + EPI_BYTES + 512);   // [4 quarters][32][2] (WIDE)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();
@@ -193,7 +198,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         const int chalf = (warp - 2) >> 2;        // column half (8-warp epilogues), else 0
         const int lane_base = ew * 32;
         unsigned char *slab = epi_smem + (size_t)(warp - 2) * SLABS_PER_WARP * SLAB_BYTES;
-        uint64_t *xbar = xin_bar + XIN * ew;
+        uint64_t *xbar = xin_bar + XIN * (warp - 2);
         uint32_t xphase = 0u;                     // one phase bit per residual slab
         int as = 0;
         uint32_t aphase = 0;
@@ -205,39 +210,30 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             const uint32_t tbase = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(as * BN);
 
             if (EPI == VG_EPI_BIAS_RESID_F32) {
-                // fp32 residual stream: 8 chunks of 32 columns; the x chunks XIN-1 ahead are in flight
-                // while chunk j is combined.  slabs [0,XIN) = x in, XIN, XIN+1 = x out, then bf16 out.
-                constexpr int NCH = BN / 32;
-                // XIN == 4: loads are issued two chunks (256 contiguous bytes per row) at a time so the
-                // DRAM controller sees longer bursts per page
-                constexpr int PRE = XIN == 4 ? 2 : XIN - 1;     // chunks issued up front
+                // fp32 residual stream in chunks of 32 columns; the x chunk one ahead is in flight while
+                // chunk j is combined.  Narrow: one warp per lane quarter takes all 8 chunks, slabs
+                // [0,2) = x in, 2,3 = x out, 4,5 = bf16 out.  WIDE: two warps per quarter take 4 chunks
+                // each, slabs [0,2) = x in, 2 = x out, 3 = bf16 out.
+                constexpr int NCH = WIDE ? 4 : BN / 32;
+                constexpr int OUT0 = XIN, XB0 = WIDE ? XIN + 1 : XIN + 2;
+                const int ch0 = WIDE ? chalf * NCH : 0;
                 if (lane == 0) {
 #pragma unroll
-                    for (int j = 0; j < PRE; ++j) {
+                    for (int j = 0; j < XIN - 1 + (WIDE ? 1 : 0); ++j) {
                         ptx::mbar_arrive_expect_tx(&xbar[j], SLAB_BYTES);
-                        ptx::tma_load_2d(slab + j * SLAB_BYTES, &tma_out, &xbar[j], col0 + j * 32, row0);
+                        ptx::tma_load_2d(slab + j * SLAB_BYTES, &tma_out, &xbar[j], col0 + (ch0 + j) * 32, row0);
                     }
                 }
                 ptx::mbar_wait(&tmem_full[as], aphase);
                 ptx::tc_fence_after();
                 float rs = 0.0f, rq = 0.0f;      // row sum / sum of squares of the new residual (LNF)
 #pragma unroll 1
-                for (int ch = 0; ch < NCH; ++ch) {
-                    const int ib = ch % XIN;
-                    if (XIN == 4) {
-                        // even iteration: chunks ch+2, ch+3 go into the slabs read in iterations ch-2, ch-1
-                        if (lane == 0 && (ch & 1) == 0 && ch + 2 < NCH) {
-#pragma unroll
-                            for (int j = 2; j < 4; ++j) {
-                                const int nb = (ch + j) % XIN;
-                                ptx::mbar_arrive_expect_tx(&xbar[nb], SLAB_BYTES);
-                                ptx::tma_load_2d(slab + nb * SLAB_BYTES, &tma_out, &xbar[nb],
-                                                 col0 + (ch + j) * 32, row0);
-                            }
-                        }
-                    } else if (lane == 0 && ch + XIN - 1 < NCH) {
-                        // that slab was fully read in iteration ch-1 (fence + __syncwarp below)
-                        const int nb = (ch + XIN - 1) % XIN;
+                for (int c = 0; c < NCH; ++c) {
+                    const int ch = ch0 + c;
+                    const int ib = c % XIN;
+                    if (!WIDE && lane == 0 && c + XIN - 1 < NCH) {
+                        // that slab was fully read in iteration c-1 (fence + __syncwarp below)
+                        const int nb = (c + XIN - 1) % XIN;
                         ptx::mbar_arrive_expect_tx(&xbar[nb], SLAB_BYTES);
                         ptx::tma_load_2d(slab + nb * SLAB_BYTES, &tma_out, &xbar[nb],
                                          col0 + (ch + XIN - 1) * 32, row0);
@@ -245,13 +241,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                     uint32_t r[32];
                     ptx::tmem_ld_32x32b_x32(tbase + (uint32_t)(ch * 32), r);
                     // the out slab about to be overwritten must have been drained by its TMA store
-                    if (lane == 0) ptx::tma_store_wait_read<1>();
+                    if (lane == 0) {
+                        if (WIDE) ptx::tma_store_wait_read<0>();
+                        else ptx::tma_store_wait_read<1>();
+                    }
                     __syncwarp();
                     ptx::mbar_wait(&xbar[ib], (xphase >> ib) & 1u);
                     xphase ^= 1u << ib;
                     ptx::tmem_ld_wait();
                     const unsigned char *xin = slab + ib * SLAB_BYTES;
-                    unsigned char *xout = slab + (XIN + obuf) * SLAB_BYTES;
+                    unsigned char *xout = slab + (OUT0 + (WIDE ? 0 : obuf)) * SLAB_BYTES;
+                    unsigned char *xb = slab + (XB0 + (WIDE ? 0 : ((c >> 1) & 1))) * SLAB_BYTES;
                     const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + col0 + ch * 32);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
@@ -268,28 +268,42 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                             rs += (o.x + o.y) + (o.z + o.w);
                             rq += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
                             // bf16 copy: two 32-column chunks share one 64-column slab row (128 B)
-                            unsigned char *xb = slab + (XIN + 2 + ((ch >> 1) & 1)) * SLAB_BYTES;
                             uint2 pk = make_uint2(pack_op(o.x, o.y), pack_op(o.z, o.w));
-                            *reinterpret_cast<uint2 *>(xb + slab_off(lane, (ch & 1) * 4 + (q >> 1)) +
+                            *reinterpret_cast<uint2 *>(xb + slab_off(lane, (c & 1) * 4 + (q >> 1)) +
                                                        (q & 1) * 8) = pk;
                         }
                     }
                     ptx::fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
+                        if (WIDE && c + XIN < NCH) {      // refill the x slab this chunk has just consumed
+                            ptx::mbar_arrive_expect_tx(&xbar[ib], SLAB_BYTES);
+                            ptx::tma_load_2d(slab + ib * SLAB_BYTES, &tma_out, &xbar[ib],
+                                             col0 + (ch + XIN) * 32, row0);
+                        }
                         ptx::tma_store_2d(&tma_out, xout, col0 + ch * 32, row0);
-                        if (LNF && (ch & 1))   // same bulk group as this chunk's fp32 store
-                            ptx::tma_store_2d(&tma_xb, slab + (XIN + 2 + ((ch >> 1) & 1)) * SLAB_BYTES,
-                                              col0 + (ch - 1) * 32, row0);
+                        if (LNF && (c & 1))   // same bulk group as this chunk's fp32 store
+                            ptx::tma_store_2d(&tma_xb, xb, col0 + (ch - 1) * 32, row0);
                         ptx::tma_store_commit();
                     }
                     obuf ^= 1;
                 }
                 if (LNF) {
+                    if (WIDE) {     // the column-half partner's partial sums, added in fixed order
+                        float2 *xs = reinterpret_cast<float2 *>(xstat) + lane_base + lane;
+                        if (chalf == 1) *xs = make_float2(rs, rq);
+                        asm volatile("bar.sync %0, 64;" ::"r"(1 + ew) : "memory");
+                        if (chalf == 0) {
+                            const float2 o = *xs;
+                            rs += o.x;
+                            rq += o.y;
+                        }
+                        asm volatile("bar.sync %0, 64;" ::"r"(1 + ew) : "memory");
+                    }
                     const int64_t row = (int64_t)row0 + lane;
                     // one slot per 256-column tile, summed in fixed order by the consumer:
                     // deterministic (no atomics) and nothing to clear between GEMMs
-                    if (row < p.M)
+                    if (row < p.M && (!WIDE || chalf == 0))
                         *reinterpret_cast<float2 *>(p.stats + 6 * row + 2 * n_blk) = make_float2(rs, rq);
                 }
             } else {
@@ -396,7 +410,7 @@ int make_tmap(VgHandle *h, CUtensorMap *map, CUtensorMapDataType dt, int elt_byt
     return VG_OK;
 }
 
-template <int EPI, bool LNF, int XIN = 2>
+template <int EPI, bool LNF, bool WIDE = false>
 int launch_t(VgHandle *h, const GemmArgs &g, cudaStream_t st)
 {
     CUtensorMap ta, tb, to, txb;
@@ -419,9 +433,9 @@ int launch_t(VgHandle *h, const GemmArgs &g, cudaStream_t st)
                        (uint64_t)g.N, 32, 64);
         if (rc) return rc;
     }
-    using Cfg = EpiCfg<EPI, LNF, XIN>;
+    using Cfg = EpiCfg<EPI, LNF, WIDE>;
     // per device and cheap: set on every launch rather than caching in process-wide state
-    VG_CUDA_CHECK(h, cudaFuncSetAttribute(gemm2_kernel<EPI, LNF, XIN>,
+    VG_CUDA_CHECK(h, cudaFuncSetAttribute(gemm2_kernel<EPI, LNF, WIDE>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)Cfg::kSmem));
     Params p{g.bias, g.colsum, g.stats, g.M, g.N, g.K};
@@ -432,7 +446,7 @@ int launch_t(VgHandle *h, const GemmArgs &g, cudaStream_t st)
                      : EPI == VG_EPI_BIAS_QGELU_BF16 ? VG_K_GEMM_FC
                      : (g.K == kMlp ? VG_K_GEMM_PROJ : VG_K_GEMM_OUT);
     VgProfScope prof(h, kind, 2.0 * (double)g.M * g.N * (double)g.K, st);
-    gemm2_kernel<EPI, LNF, XIN><<<2 * clusters, Cfg::kThreads, Cfg::kSmem, st>>>(ta, tb, to, txb, p);
+    gemm2_kernel<EPI, LNF, WIDE><<<2 * clusters, Cfg::kThreads, Cfg::kSmem, st>>>(ta, tb, to, txb, p);
     VG_LAUNCH_CHECK(h);
     return VG_OK;
 }
@@ -457,8 +471,8 @@ int launch_gemm_2cta(VgHandle *h, const GemmArgs &g, cudaStream_t st)
             return lnf ? launch_t<VG_EPI_BIAS_QGELU_BF16, true>(h, g, st)
                        : launch_t<VG_EPI_BIAS_QGELU_BF16, false>(h, g, st);
         case VG_EPI_BIAS_RESID_F32:
-            if (lnf && g.K <= kWidth)   // out-proj: HBM bound -> deep residual prefetch, 3 operand stages
-                return launch_t<VG_EPI_BIAS_RESID_F32, true, 4>(h, g, st);
+            if (lnf && g.K <= kWidth && !getenv("VG_GEMM_NARROW"))   // out-proj: epilogue bound -> 8 warps
+                return launch_t<VG_EPI_BIAS_RESID_F32, true, true>(h, g, st);
             return lnf ? launch_t<VG_EPI_BIAS_RESID_F32, true>(h, g, st)
                        : launch_t<VG_EPI_BIAS_RESID_F32, false>(h, g, st);
     }
