@@ -44,18 +44,23 @@ constexpr int SLAB_BYTES = 4096;              // 32 rows x 128 B, SWIZZLE_128B
 //   bf16 epilogues     : A is the RAW residual stream in bf16, W carries the LayerNorm gain, and the
 //                        normalisation is applied after the matmul:
 //                        y = rstd_i * (acc - mu_i * colsum_n) + c_n      (model.py:157-163,190-191)
-// WIDE (residual epilogue only): the K = 768 out-proj GEMM moves 9 KB of residual traffic per row for
-// 0.23 GFLOP per image-layer, so its epilogue (not the tensor pipe) sets the pace: 8 epilogue warps,
-// two per TMEM lane quarter with half of the columns each, paid for with one operand stage.
-template <int EPI, bool LNF, bool WIDE = false> struct EpiCfg {
+// RMODE (residual epilogue only) trades epilogue resources against operand stages:
+//   kNarrow  4 warps, double-buffered out slabs, 4 operand stages          (non-LN-folded path, tests)
+//   kWide    8 warps (two per TMEM lane quarter, half of the columns each), single out slabs, 3 stages:
+//            the K = 768 out-proj GEMM moves 9 KB of residual traffic per row for 0.23 GFLOP per
+//            image-layer, so its epilogue (not the tensor pipe) sets the pace
+//   kDeep    4 warps, single out slabs, 5 stages: the K = 3072 c_proj GEMM is tensor bound and streams
+//            11 GB per launch next to its operands, so it wants the deeper TMA ring instead
+enum : int { kNarrow = 0, kWide = 1, kDeep = 2 };
+template <int EPI, bool LNF, int RMODE = kNarrow> struct EpiCfg {
     static constexpr bool kResid = EPI == VG_EPI_BIAS_RESID_F32;
-    static constexpr int kWarps = kResid ? (WIDE ? 8 : 4) : 8;
-    // f32 residual: 2 in + 2 out (+ 2 bf16 out); WIDE: 2 in + 1 out + 1 bf16 out per warp
-    static constexpr int kSlabs = kResid ? (WIDE ? 4 : 2 + 2 + (LNF ? 2 : 0)) : 2;
+    static constexpr bool kSlim = RMODE != kNarrow;          // 2 in + 1 out + 1 bf16 out per warp
+    static constexpr int kWarps = kResid ? (RMODE == kWide ? 8 : 4) : 8;
+    static constexpr int kSlabs = kResid ? (kSlim ? 4 : 2 + 2 + (LNF ? 2 : 0)) : 2;
     static constexpr int kThreads = 64 + 32 * kWarps;
-    static constexpr int kStages = kResid ? (WIDE ? 3 : 4) : 5;   // bf16 epilogues: 32 KiB to spare
+    static constexpr int kStages = kResid ? (RMODE == kWide ? 3 : RMODE == kDeep ? 5 : 4) : 5;
     static constexpr int kEpiBytes = kWarps * kSlabs * SLAB_BYTES;          // 64 / 96 / 128 KiB
-    static constexpr int kXchgBytes = WIDE ? 4 * 32 * 2 * 4 : 0;           // row-statistics hand-off
+    static constexpr int kXchgBytes = RMODE == kWide ? 4 * 32 * 2 * 4 : 0;   // row-statistics hand-off
     static constexpr size_t kSmem = (size_t)kStages * STAGE_BYTES + kEpiBytes + 1024 + 512 + kXchgBytes;
 };
 
@@ -78,13 +83,14 @@ __device__ __forceinline__ float quick_gelu(float v)
 // 16-byte chunk c of row r inside a 1024-byte-aligned SWIZZLE_128B slab
 __device__ __forceinline__ uint32_t slab_off(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
 
-template <int EPI, bool LNF, bool WIDE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<EPI, LNF, WIDE>::kThreads, 1)
+template <int EPI, bool LNF, int RMODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<EPI, LNF, RMODE>::kThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
              const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_xb,
              const Params p)
 {
-    using Cfg = EpiCfg<EPI, LNF, WIDE>;
+    using Cfg = EpiCfg<EPI, LNF, RMODE>;
+    constexpr bool WIDE = RMODE == kWide, SLIM = RMODE != kNarrow;
     constexpr int XIN = 2;       // fp32 residual slabs in flight per epilogue warp
     constexpr int STAGES = Cfg::kStages;
     constexpr int EPI_BYTES = Cfg::kEpiBytes;
@@ -212,14 +218,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             if (EPI == VG_EPI_BIAS_RESID_F32) {
                 // fp32 residual stream in chunks of 32 columns; the x chunk one ahead is in flight while
                 // chunk j is combined.  Narrow: one warp per lane quarter takes all 8 chunks, slabs
-                // [0,2) = x in, 2,3 = x out, 4,5 = bf16 out.  WIDE: two warps per quarter take 4 chunks
-                // each, slabs [0,2) = x in, 2 = x out, 3 = bf16 out.
+                // [0,2) = x in, 2,3 = x out, 4,5 = bf16 out.  Slim (wide / deep): slabs [0,2) = x in,
+                // 2 = x out, 3 = bf16 out; wide: two warps per quarter take 4 chunks each.
                 constexpr int NCH = WIDE ? 4 : BN / 32;
-                constexpr int OUT0 = XIN, XB0 = WIDE ? XIN + 1 : XIN + 2;
+                constexpr int OUT0 = XIN, XB0 = SLIM ? XIN + 1 : XIN + 2;
                 const int ch0 = WIDE ? chalf * NCH : 0;
                 if (lane == 0) {
 #pragma unroll
-                    for (int j = 0; j < XIN - 1 + (WIDE ? 1 : 0); ++j) {
+                    for (int j = 0; j < XIN - 1 + (SLIM ? 1 : 0); ++j) {
                         ptx::mbar_arrive_expect_tx(&xbar[j], SLAB_BYTES);
                         ptx::tma_load_2d(slab + j * SLAB_BYTES, &tma_out, &xbar[j], col0 + (ch0 + j) * 32, row0);
                     }
@@ -231,7 +237,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                 for (int c = 0; c < NCH; ++c) {
                     const int ch = ch0 + c;
                     const int ib = c % XIN;
-                    if (!WIDE && lane == 0 && c + XIN - 1 < NCH) {
+                    if (!SLIM && lane == 0 && c + XIN - 1 < NCH) {
                         // that slab was fully read in iteration c-1 (fence + __syncwarp below)
                         const int nb = (c + XIN - 1) % XIN;
                         ptx::mbar_arrive_expect_tx(&xbar[nb], SLAB_BYTES);
@@ -242,7 +248,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                     ptx::tmem_ld_32x32b_x32(tbase + (uint32_t)(ch * 32), r);
                     // the out slab about to be overwritten must have been drained by its TMA store
                     if (lane == 0) {
-                        if (WIDE) ptx::tma_store_wait_read<0>();
+                        if (SLIM) ptx::tma_store_wait_read<0>();
                         else ptx::tma_store_wait_read<1>();
                     }
                     __syncwarp();
@@ -250,8 +256,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                     xphase ^= 1u << ib;
                     ptx::tmem_ld_wait();
                     const unsigned char *xin = slab + ib * SLAB_BYTES;
-                    unsigned char *xout = slab + (OUT0 + (WIDE ? 0 : obuf)) * SLAB_BYTES;
-                    unsigned char *xb = slab + (XB0 + (WIDE ? 0 : ((c >> 1) & 1))) * SLAB_BYTES;
+                    unsigned char *xout = slab + (OUT0 + (SLIM ? 0 : obuf)) * SLAB_BYTES;
+                    unsigned char *xb = slab + (XB0 + (SLIM ? 0 : ((c >> 1) & 1))) * SLAB_BYTES;
                     const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + col0 + ch * 32);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
@@ -276,7 +282,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                     ptx::fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        if (WIDE && c + XIN < NCH) {      // refill the x slab this chunk has just consumed
+                        if (SLIM && c + XIN < NCH) {      // refill the x slab this chunk has just consumed
                             ptx::mbar_arrive_expect_tx(&xbar[ib], SLAB_BYTES);
                             ptx::tma_load_2d(slab + ib * SLAB_BYTES, &tma_out, &xbar[ib],
                                              col0 + (ch + XIN) * 32, row0);
@@ -410,7 +416,7 @@ int make_tmap(VgHandle *h, CUtensorMap *map, CUtensorMapDataType dt, int elt_byt
     return VG_OK;
 }
 
-template <int EPI, bool LNF, bool WIDE = false>
+template <int EPI, bool LNF, int RMODE = kNarrow>
 int launch_t(VgHandle *h, const GemmArgs &g, cudaStream_t st)
 {
     CUtensorMap ta, tb, to, txb;
@@ -433,9 +439,9 @@ int launch_t(VgHandle *h, const GemmArgs &g, cudaStream_t st)
                        (uint64_t)g.N, 32, 64);
         if (rc) return rc;
     }
-    using Cfg = EpiCfg<EPI, LNF, WIDE>;
+    using Cfg = EpiCfg<EPI, LNF, RMODE>;
     // per device and cheap: set on every launch rather than caching in process-wide state
-    VG_CUDA_CHECK(h, cudaFuncSetAttribute(gemm2_kernel<EPI, LNF, WIDE>,
+    VG_CUDA_CHECK(h, cudaFuncSetAttribute(gemm2_kernel<EPI, LNF, RMODE>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)Cfg::kSmem));
     Params p{g.bias, g.colsum, g.stats, g.M, g.N, g.K};
@@ -446,7 +452,7 @@ int launch_t(VgHandle *h, const GemmArgs &g, cudaStream_t st)
                      : EPI == VG_EPI_BIAS_QGELU_BF16 ? VG_K_GEMM_FC
                      : (g.K == kMlp ? VG_K_GEMM_PROJ : VG_K_GEMM_OUT);
     VgProfScope prof(h, kind, 2.0 * (double)g.M * g.N * (double)g.K, st);
-    gemm2_kernel<EPI, LNF, WIDE><<<2 * clusters, Cfg::kThreads, Cfg::kSmem, st>>>(ta, tb, to, txb, p);
+    gemm2_kernel<EPI, LNF, RMODE><<<2 * clusters, Cfg::kThreads, Cfg::kSmem, st>>>(ta, tb, to, txb, p);
     VG_LAUNCH_CHECK(h);
     return VG_OK;
 }
@@ -472,7 +478,9 @@ int launch_gemm_2cta(VgHandle *h, const GemmArgs &g, cudaStream_t st)
                        : launch_t<VG_EPI_BIAS_QGELU_BF16, false>(h, g, st);
         case VG_EPI_BIAS_RESID_F32:
             if (lnf && g.K <= kWidth && !getenv("VG_GEMM_NARROW"))   // out-proj: epilogue bound -> 8 warps
-                return launch_t<VG_EPI_BIAS_RESID_F32, true, true>(h, g, st);
+                return launch_t<VG_EPI_BIAS_RESID_F32, true, kWide>(h, g, st);
+            if (lnf && !getenv("VG_GEMM_NARROW"))                    // c_proj: tensor bound -> 5-stage ring
+                return launch_t<VG_EPI_BIAS_RESID_F32, true, kDeep>(h, g, st);
             return lnf ? launch_t<VG_EPI_BIAS_RESID_F32, true>(h, g, st)
                        : launch_t<VG_EPI_BIAS_RESID_F32, false>(h, g, st);
     }
