@@ -178,6 +178,7 @@ struct GemmArgs {
 constexpr int kEpiPatch = 3;  // out fp32 x[img*197 + 1 + p][n] = acc + table[1+p][n]
 int launch_gemm(VgHandle *h, const GemmArgs &g, cudaStream_t st);
 int launch_gemm_2cta(VgHandle *h, const GemmArgs &g, cudaStream_t st);   // cta_group::2 path
+int launch_gemm_patch_2cta(VgHandle *h, const GemmArgs &g, cudaStream_t st);   // patch embedding on the same kernel
 
 int launch_attention(VgHandle *h, const op_t *qkv, int64_t B, op_t *out,
                      cudaStream_t st);

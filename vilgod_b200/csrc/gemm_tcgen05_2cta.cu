@@ -83,7 +83,7 @@ __device__ __forceinline__ float quick_gelu(float v)
 // 16-byte chunk c of row r inside a 1024-byte-aligned SWIZZLE_128B slab
 __device__ __forceinline__ uint32_t slab_off(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
 
-template <int EPI, bool LNF, int RMODE>
+template <int EPI, bool LNF, int RMODE, bool PATCH>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<EPI, LNF, RMODE>::kThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
              const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_xb,
@@ -113,16 +113,21 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     const uint32_t rank = ptx::cluster_ctarank();
     const bool leader = rank == 0;
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-    const int m_tiles = (int)((p.M + 2 * BM - 1) / (2 * BM));
+    // PATCH: one pair tile = the 196 patch rows of one image (rows 196..255 are zero-filled by TMA and
+    // clipped on the way out), so that token = 1 + row never straddles two images
+    const int m_tiles = PATCH ? (int)(p.M / kPatches) : (int)((p.M + 2 * BM - 1) / (2 * BM));
     const int n_tiles = p.N / BN;
     const int num_tiles = m_tiles * n_tiles;
     const int num_kb = p.K / BK;
+    // fp32 rows added in the residual epilogue: the residual stream itself, or (PATCH) the
+    // [197,768] table b_eff + positional embedding, whose map travels in the tma_xb slot
+    const CUtensorMap *xin_map = PATCH ? &tma_xb : &tma_out;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tma_a);
         ptx::prefetch_tensormap(&tma_b);
         ptx::prefetch_tensormap(&tma_out);
-        if (EPI == VG_EPI_BIAS_RESID_F32 && LNF) ptx::prefetch_tensormap(&tma_xb);
+        if (EPI == VG_EPI_BIAS_RESID_F32 && (LNF || PATCH)) ptx::prefetch_tensormap(&tma_xb);
         for (int s = 0; s < STAGES; ++s) {
             ptx::mbar_init(&full_bar[s], 1);
             ptx::mbar_init(&empty_bar[s], 1);
@@ -157,7 +162,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
                     unsigned char *sa = smem + (size_t)stage * STAGE_BYTES;
                     if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
-                    ptx::tma_load_2d_pair(sa, &tma_a, &full_bar[stage], kb * BK, a_row);
+                    if (PATCH) ptx::tma_load_3d_pair(sa, &tma_a, &full_bar[stage], kb * BK, (int)rank * BM, m_blk);
+                    else ptx::tma_load_2d_pair(sa, &tma_a, &full_bar[stage], kb * BK, a_row);
                     ptx::tma_load_2d_pair(sa + A_BYTES, &tma_b, &full_bar[stage], kb * BK, b_row);
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -211,7 +217,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         int obuf = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
             const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
-            const int row0 = m_blk * 2 * BM + (int)rank * BM + lane_base;   // first row of the slab
+            // first row of the slab; PATCH: token index inside image m_blk
+            const int row0 = PATCH ? 1 + (int)rank * BM + lane_base : m_blk * 2 * BM + (int)rank * BM + lane_base;
+            if (PATCH && (int)rank * BM + lane_base >= kPatches) {   // no patch row in this warp's lanes
+                ptx::mbar_wait(&tmem_full[as], aphase);
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive_remote(&tmem_empty[as], 0);
+                if (++as == ACC_STAGES) { as = 0; aphase ^= 1u; }
+                continue;
+            }
             const int col0 = n_blk * BN;
             const uint32_t tbase = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(as * BN);
 
@@ -227,7 +242,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < XIN - 1 + (SLIM ? 1 : 0); ++j) {
                         ptx::mbar_arrive_expect_tx(&xbar[j], SLAB_BYTES);
-                        ptx::tma_load_2d(slab + j * SLAB_BYTES, &tma_out, &xbar[j], col0 + (ch0 + j) * 32, row0);
+                        ptx::tma_load_2d(slab + j * SLAB_BYTES, xin_map, &xbar[j], col0 + (ch0 + j) * 32, row0);
                     }
                 }
                 ptx::mbar_wait(&tmem_full[as], aphase);
@@ -241,7 +256,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                         // that slab was fully read in iteration c-1 (fence + __syncwarp below)
                         const int nb = (c + XIN - 1) % XIN;
                         ptx::mbar_arrive_expect_tx(&xbar[nb], SLAB_BYTES);
-                        ptx::tma_load_2d(slab + nb * SLAB_BYTES, &tma_out, &xbar[nb],
+                        ptx::tma_load_2d(slab + nb * SLAB_BYTES, xin_map, &xbar[nb],
                                          col0 + (ch + XIN - 1) * 32, row0);
                     }
                     uint32_t r[32];
@@ -263,7 +278,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                     for (int q = 0; q < 8; ++q) {
                         const uint32_t off = slab_off(lane, q);
                         const float4 x = *reinterpret_cast<const float4 *>(xin + off);
-                        const float4 bv = __ldg(b4 + q);
+                        const float4 bv = PATCH ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(b4 + q);
                         float4 o;
                         o.x = x.x + (__uint_as_float(r[4 * q + 0]) + bv.x);
                         o.y = x.y + (__uint_as_float(r[4 * q + 1]) + bv.y);
@@ -284,10 +299,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                     if (lane == 0) {
                         if (SLIM && c + XIN < NCH) {      // refill the x slab this chunk has just consumed
                             ptx::mbar_arrive_expect_tx(&xbar[ib], SLAB_BYTES);
-                            ptx::tma_load_2d(slab + ib * SLAB_BYTES, &tma_out, &xbar[ib],
+                            ptx::tma_load_2d(slab + ib * SLAB_BYTES, xin_map, &xbar[ib],
                                              col0 + (ch + XIN) * 32, row0);
                         }
-                        ptx::tma_store_2d(&tma_out, xout, col0 + ch * 32, row0);
+                        if (PATCH) ptx::tma_store_3d(&tma_out, xout, col0 + ch * 32, row0, m_blk);
+                        else ptx::tma_store_2d(&tma_out, xout, col0 + ch * 32, row0);
                         if (LNF && (c & 1))   // same bulk group as this chunk's fp32 store
                             ptx::tma_store_2d(&tma_xb, xb, col0 + (ch - 1) * 32, row0);
                         ptx::tma_store_commit();
@@ -441,7 +457,7 @@ int launch_t(VgHandle *h, const GemmArgs &g, cudaStream_t st)
     }
     using Cfg = EpiCfg<EPI, LNF, RMODE>;
     // per device and cheap: set on every launch rather than caching in process-wide state
-    VG_CUDA_CHECK(h, cudaFuncSetAttribute(gemm2_kernel<EPI, LNF, RMODE>,
+    VG_CUDA_CHECK(h, cudaFuncSetAttribute(gemm2_kernel<EPI, LNF, RMODE, false>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)Cfg::kSmem));
     Params p{g.bias, g.colsum, g.stats, g.M, g.N, g.K};
@@ -452,12 +468,69 @@ int launch_t(VgHandle *h, const GemmArgs &g, cudaStream_t st)
                      : EPI == VG_EPI_BIAS_QGELU_BF16 ? VG_K_GEMM_FC
                      : (g.K == kMlp ? VG_K_GEMM_PROJ : VG_K_GEMM_OUT);
     VgProfScope prof(h, kind, 2.0 * (double)g.M * g.N * (double)g.K, st);
-    gemm2_kernel<EPI, LNF, RMODE><<<2 * clusters, Cfg::kThreads, Cfg::kSmem, st>>>(ta, tb, to, txb, p);
+    gemm2_kernel<EPI, LNF, RMODE, false><<<2 * clusters, Cfg::kThreads, Cfg::kSmem, st>>>(ta, tb, to, txb, p);
     VG_LAUNCH_CHECK(h);
     return VG_OK;
 }
 
+int make_tmap3(VgHandle *h, CUtensorMap *map, CUtensorMapDataType dt, int elt_bytes, const void *ptr,
+               uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1)
+{
+    auto encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(h->tma_encode);
+    if (!encode) {
+        VG_SET_ERR(h, "cuTensorMapEncodeTiled entry point unavailable");
+        return VG_ECUDA;
+    }
+    const cuuint64_t gdim[3] = {d0, d1, d2};
+    const cuuint64_t gstride[2] = {d0 * (uint64_t)elt_bytes, d0 * d1 * (uint64_t)elt_bytes};
+    const cuuint32_t box[3] = {box0, box1, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(map, dt, 3, const_cast<void *>(ptr), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        VG_SET_ERR(h, "cuTensorMapEncodeTiled (3-D) failed (CUresult %d)", (int)r);
+        return VG_ECUDA;
+    }
+    return VG_OK;
+}
+
 }  // namespace
+
+// Patch embedding (model.py:223-229 with the preprocessing folded in):
+//   x[img][1 + p][:] = tiles[img][p][:] . W_eff^T + table[1 + p][:]
+// on the 2-CTA kernel: A is a 3-D map [img][196][256] tiled per image, the "residual" read is the
+// [197,768] table (L2 resident) and the store goes through a 3-D map [img][197][768] that clips the
+// rows beyond token 196.  The class-token row is written by ln_pre.
+int launch_gemm_patch_2cta(VgHandle *h, const GemmArgs &g, cudaStream_t st)
+{
+    if (g.M % kPatches != 0 || g.N != kWidth || g.K != kPatchK) {
+        VG_SET_ERR(h, "patch GEMM: unexpected shape M=%lld N=%d K=%d", (long long)g.M, g.N, g.K);
+        return VG_ESHAPE;
+    }
+    const uint64_t B = (uint64_t)(g.M / kPatches);
+    CUtensorMap ta, tb, to, ttab;
+    int rc = make_tmap3(h, &ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.a, kPatchK, kPatches, B, BK, BM);
+    if (rc) return rc;
+    rc = make_tmap(h, &tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.w, (uint64_t)g.N, (uint64_t)g.K, BN / 2, BK);
+    if (rc) return rc;
+    rc = make_tmap3(h, &to, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.out, kWidth, kTokens, B, 32, 32);
+    if (rc) return rc;
+    rc = make_tmap(h, &ttab, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.bias, kTokens, kWidth, 32, 32);
+    if (rc) return rc;
+    using Cfg = EpiCfg<VG_EPI_BIAS_RESID_F32, false, kWide>;
+    auto kern = gemm2_kernel<VG_EPI_BIAS_RESID_F32, false, kWide, true>;
+    VG_CUDA_CHECK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
+    Params p{nullptr, nullptr, nullptr, g.M, g.N, g.K};
+    const int64_t tiles = (int64_t)B * (g.N / BN);
+    const int max_clusters = h->num_sms / 2;
+    const int clusters = (int)(tiles < max_clusters ? tiles : max_clusters);
+    // credited with the un-folded K = 3*16*16
+    VgProfScope prof(h, VG_K_GEMM_PATCH, 2.0 * (double)g.M * g.N * 768.0, st);
+    kern<<<2 * clusters, Cfg::kThreads, Cfg::kSmem, st>>>(ta, tb, to, ttab, p);
+    VG_LAUNCH_CHECK(h);
+    return VG_OK;
+}
 
 int launch_gemm_2cta(VgHandle *h, const GemmArgs &g, cudaStream_t st)
 {

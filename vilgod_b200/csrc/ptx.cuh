@@ -226,6 +226,24 @@ __device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorM
         "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_pair(void *smem_dst, const CUtensorMap *m, uint64_t *bar,
+                                                 int32_t c0, int32_t c1, int32_t c2)
+{
+    const uint32_t bar_addr = smem_u32(bar) & 0xFEFFFFFFu;
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *m, const void *smem_src, int32_t c0,
+                                             int32_t c1, int32_t c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
 // TMA store shared -> global (bulk async-group completion)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *m, const void *smem_src, int32_t c0,
                                              int32_t c1)
