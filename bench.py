@@ -321,7 +321,7 @@ def run_ours(a):
         tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-        roofline = {"bound": "tensor", "kernel": "gemm2_kernel<EPI,LNF> (2-CTA tcgen05; QKV / out-proj / c_fc / c_proj) + gemm_kernel<patch>",
+        roofline = {"bound": "tensor", "kernel": "gemm2_kernel<EPI,LNF,RMODE,PATCH> (2-CTA tcgen05: patch-embed / QKV / out-proj / c_fc / c_proj)",
                     "achieved": gemm_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": gemm_tflops / peaks["bf16_tflops"], "traffic": traffic,
                     "peak_source": peaks["source"], "launches": g_n,
