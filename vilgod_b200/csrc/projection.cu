@@ -184,6 +184,12 @@ __device__ __forceinline__ float warp_min(float v)
     for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+__device__ __forceinline__ float max3f(float a, float b, float c)
+{
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
 __device__ __forceinline__ float4 max4(float4 a, float4 b)
 {
     return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
@@ -307,6 +313,8 @@ __global__ void __launch_bounds__(NT, 2) projection_kernel(const ProjParams P)
         return;
     }
     if (P.status && v == 0 && tid == 0) P.status[c] = VG_OK;
+    for (int i = tid; i < R * R / 4; i += NT)       // the one clear of the grid buffer (phase 3)
+        reinterpret_cast<float4 *>(sm.G)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     Quant qn;
     qn.cx = sm.norm[0]; qn.cy = sm.norm[1]; qn.cz = sm.norm[2]; qn.pr = sm.norm[3];
     qn.rc_pr = __frcp_rn(qn.pr);
@@ -383,9 +391,17 @@ __global__ void __launch_bounds__(NT, 2) projection_kernel(const ProjParams P)
     for (int k = 0; k < 9; ++k) w[k] = P.gauss[k];
 
     // ---- phase 3: per occupied slice: scatter-max, 5x5 max-pool, 3x3 Gaussian, depth max --------
-    // Only the rows a slice can influence are touched: points in rows [ylo, yhi] spread to pooled
-    // rows [ylo-3, yhi+1] and smoothed rows [ylo-4, yhi+2]; the band [ylo-5, yhi+4] is cleared so
-    // every halo row the stencils read is zero.  Stale rows outside the band are never read.
+    // The grid buffer is cleared ONCE.  Slices are visited in increasing depth and a point of slice d
+    // carries a value in (d-1, d], so whatever lower slices left behind is <= d-1: scatter-max simply
+    // overwrites it, and after pooling (max commutes with the monotone cut) everything <= d-1 is cut
+    // to the 0 an empty cell holds.  Only slices whose values can tie with a lower one (0/1: both 1.0,
+    // 7: 6.0 like the top of slice 6 -- both only reachable through rounding) clear again.
+    // Per slice that leaves two block barriers: scatter | fused stencil pass.  In the fused pass a warp
+    // owns a chunk of smoothed rows and streams the raw rows it needs through registers: horizontal
+    // 5-max (shuffles), vertical 5-max over a ring of 5 rows, cut, 3x3 Gaussian over a ring of 3
+    // pooled rows, running depth max into IMG.  Rows outside [ylo, yhi] hold no point of the slice and
+    // are not even loaded.
+    bool dirty = false;       // G holds values of a lower slice
     for (int d = 0; d < D; ++d) {
         if (!((mask >> d) & 1u)) {
             if (P.dbg_grid) {
@@ -395,10 +411,17 @@ __global__ void __launch_bounds__(NT, 2) projection_kernel(const ProjParams P)
             continue;
         }
         const int ylo = sm.ylo[d], yhi = sm.yhi[d];
-        const int blo = max(ylo - 5, 0), bhi = min(yhi + 4, R - 1);
-        for (int i = tid; i < (bhi - blo + 1) * (R / 4); i += NT)
-            reinterpret_cast<float4 *>(sm.G + blo * R)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        __syncthreads();
+        float thr = 0.0f;
+        if (dirty) {
+            if (d >= 2 && d <= D - 2) {
+                thr = (float)(d - 1);
+            } else {
+                for (int i = tid; i < R * R / 4; i += NT)
+                    reinterpret_cast<float4 *>(sm.G)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                __syncthreads();
+            }
+        }
+        dirty = true;
         {
             const int ncache = min(n, CAP);
             for (int i = tid; i < ncache; i += NT) {
@@ -431,87 +454,71 @@ __global__ void __launch_bounds__(NT, 2) projection_kernel(const ProjParams P)
         if (P.dbg_grid) {
             float *g = P.dbg_grid + ((size_t)b * D + d) * R * R;
             for (int i = tid; i < R * R; i += NT) {
-                const int y = i / R;
-                g[i] = (y >= blo && y <= bhi) ? sm.G[i] : 0.0f;
+                const float t = sm.G[i];
+                g[i] = t > thr ? t : 0.0f;
             }
-            __syncthreads();
         }
 
-        // horizontal 5-max in place, one warp per row: H(y,x) = max G(y, x-1..x+3), x in [0,110)
-        for (int y = ylo + warp; y <= yhi; y += NW) {
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (lane < R / 4) a = reinterpret_cast<const float4 *>(sm.G + y * R)[lane];
-            const float left = __shfl_up_sync(0xffffffffu, a.w, 1);
-            const float rx = __shfl_down_sync(0xffffffffu, a.x, 1);
-            const float ry = __shfl_down_sync(0xffffffffu, a.y, 1);
-            const float rz = __shfl_down_sync(0xffffffffu, a.z, 1);
-            const float l = lane == 0 ? 0.0f : left;
-            const float m_yz = fmaxf(a.y, a.z), m_zw = fmaxf(a.z, a.w);
-            const float m_xyz = fmaxf(a.x, m_yz), m_yzw = fmaxf(a.y, m_zw);
-            float4 hmx;
-            hmx.x = fmaxf(fmaxf(l, a.w), m_xyz);
-            hmx.y = fmaxf(fmaxf(a.x, rx), m_yzw);
-            hmx.z = fmaxf(m_yzw, fmaxf(rx, ry));
-            hmx.w = fmaxf(m_zw, fmaxf(fmaxf(rx, ry), rz));
-            if (lane == R / 4 - 1) { hmx.z = 0.0f; hmx.w = 0.0f; }   // columns 110, 111: padding
-            __syncwarp();
-            if (lane < R / 4) reinterpret_cast<float4 *>(sm.G + y * R)[lane] = hmx;
-        }
-        __syncthreads();
-
-        // vertical 5-max in place: warp = 7-row chunk, lane = 4-column group.
-        // P(y,x) = max H(y-1..y+3, x); all loads precede all stores (barrier in between).
         {
-            const int vlo = max(ylo - 3, 0), vhi = min(yhi + 1, R - 1);
-            const int y0 = vlo + warp * CH;
-            const bool active = y0 <= vhi && lane < R / 4;      // idle chunks only keep the barrier
-            float4 o[CH];
-            if (active) {
-                float4 h[CH + 4];
-#pragma unroll
-                for (int k = 0; k < CH + 4; ++k) {
-                    const int y = y0 - 1 + k;
-                    h[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (y >= 0 && y < R) h[k] = reinterpret_cast<const float4 *>(sm.G + y * R)[lane];
-                }
-#pragma unroll
-                for (int k = 0; k < CH; ++k) {
-                    o[k] = max4(max4(max4(h[k], h[k + 1]), max4(h[k + 2], h[k + 3])), h[k + 4]);
-                    if (y0 + k >= Q) o[k] = make_float4(0.f, 0.f, 0.f, 0.f);   // rows 110, 111: padding
-                }
-            }
-            __syncthreads();      // every load of the in-place pass precedes every store
-            if (active) {
-#pragma unroll
-                for (int k = 0; k < CH; ++k)
-                    if (y0 + k <= vhi) reinterpret_cast<float4 *>(sm.G + (y0 + k) * R)[lane] = o[k];
-            }
-        }
-        __syncthreads();
-
-        // 3x3 Gaussian (zero padding) and running max over depth into IMG.
-        // acc = fma(w[i][j], P(y+i-1, x+j-1), acc) in row-major tap order.
-        {
-            const int glo = max(ylo - 4, 0), ghi = min(yhi + 2, Q - 1);
-            const int y0 = glo + warp * CH;
+            const int glo = max(ylo - 4, 0), ghi = min(yhi + 2, Q - 1);   // smoothed rows of this slice
+            const int ch = max((ghi - glo + NW) / NW, 2);                 // rows per warp, 2..7
+            const int y0 = glo + warp * ch;
             if (y0 <= ghi) {
-                float4 pa, pb, pc;          // rows y-1, y, y+1
-                float la, lb, lc, ra, rb, rc;
-                auto load_row = [&](int y, float4 &p, float &l, float &r) {
-                    p = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (lane < R / 4 && y >= 0 && y < Q)
-                        p = reinterpret_cast<const float4 *>(sm.G + y * R)[lane];
-                    l = __shfl_up_sync(0xffffffffu, p.w, 1);
-                    r = __shfl_down_sync(0xffffffffu, p.x, 1);
-                    if (lane == 0) l = 0.0f;
-                };
-                load_row(y0 - 1, pa, la, ra);
-                load_row(y0, pb, lb, rb);
+                const int y1 = min(y0 + ch - 1, ghi);
+                float4 h0, h1, h2, h3, h4;                 // horizontal maxima of raw rows r-4 .. r
+                float4 pa, pb, pc;                         // pooled rows q-2, q-1, q
+                float la, lb, lc, ra, rb, rc;              // their left / right neighbour columns
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                h0 = h1 = h2 = h3 = h4 = z4;
+                pa = pb = pc = z4;
+                la = lb = lc = ra = rb = rc = 0.0f;
 #pragma unroll
-                for (int k = 0; k < CH; ++k) {
-                    const int y = y0 + k;
-                    if (y > ghi) break;        // warp-uniform
-                    load_row(y + 1, pc, lc, rc);
+                for (int i = 0; i < CH + 6; ++i) {
+                    const int r = y0 - 2 + i;              // raw row streamed in this step
+                    if (r > y1 + 4) break;                 // warp-uniform
+                    // H(r, x) = max G(r, x-1 .. x+3) for x in [0, 110); columns 110, 111 are padding
+                    float4 h = z4;
+                    if (r >= ylo && r <= yhi) {            // warp-uniform: other rows hold no point of d
+                        float4 a = z4;
+                        if (lane < R / 4) a = reinterpret_cast<const float4 *>(sm.G + r * R)[lane];
+                        const float left = __shfl_up_sync(0xffffffffu, a.w, 1);
+                        const float rx = __shfl_down_sync(0xffffffffu, a.x, 1);
+                        const float ry = __shfl_down_sync(0xffffffffu, a.y, 1);
+                        const float rz = __shfl_down_sync(0xffffffffu, a.z, 1);
+                        const float l = lane == 0 ? 0.0f : left;
+                        const float m3 = max3f(a.z, a.w, rx);
+                        h.x = max3f(max3f(l, a.x, a.y), a.z, a.w);
+                        h.y = max3f(m3, a.x, a.y);
+                        h.z = max3f(m3, a.y, ry);
+                        h.w = max3f(m3, ry, rz);
+                        if (lane == R / 4 - 1) { h.z = 0.0f; h.w = 0.0f; }
+                    }
+                    h0 = h1; h1 = h2; h2 = h3; h3 = h4; h4 = h;
+                    if (i < 4) continue;
+                    // P(q, x) = max H(q-1 .. q+3, x), q = r - 3; rows 110, 111 are padding; cut the
+                    // leftovers of lower slices
+                    const int q = r - 3;
+                    float4 pl = z4;
+                    if (q >= 0 && q < Q) {
+                        pl.x = max3f(max3f(h0.x, h1.x, h2.x), h3.x, h4.x);
+                        pl.y = max3f(max3f(h0.y, h1.y, h2.y), h3.y, h4.y);
+                        pl.z = max3f(max3f(h0.z, h1.z, h2.z), h3.z, h4.z);
+                        pl.w = max3f(max3f(h0.w, h1.w, h2.w), h3.w, h4.w);
+                        pl.x = pl.x > thr ? pl.x : 0.0f;
+                        pl.y = pl.y > thr ? pl.y : 0.0f;
+                        pl.z = pl.z > thr ? pl.z : 0.0f;
+                        pl.w = pl.w > thr ? pl.w : 0.0f;
+                    }
+                    pa = pb; la = lb; ra = rb;
+                    pb = pc; lb = lc; rb = rc;
+                    pc = pl;
+                    lc = __shfl_up_sync(0xffffffffu, pl.w, 1);
+                    rc = __shfl_down_sync(0xffffffffu, pl.x, 1);
+                    if (lane == 0) lc = 0.0f;
+                    if (i < 6) continue;
+                    // 3x3 Gaussian (zero padding) of pooled rows y-1, y, y+1 (y = r - 4) as a row-major
+                    // FMA chain, then the running max over depth
+                    const int y = r - 4;
                     const float ta[6] = {la, pa.x, pa.y, pa.z, pa.w, ra};
                     const float tb[6] = {lb, pb.x, pb.y, pb.z, pb.w, rb};
                     const float tc[6] = {lc, pc.x, pc.y, pc.z, pc.w, rc};
@@ -534,8 +541,6 @@ __global__ void __launch_bounds__(NT, 2) projection_kernel(const ProjParams P)
                         float4 *dst = reinterpret_cast<float4 *>(sm.IMG + y * R) + lane;
                         *dst = max4(*dst, make_float4(o[0], o[1], o[2], o[3]));
                     }
-                    pa = pb; la = lb; ra = rb;
-                    pb = pc; lb = lc; rb = rc;
                 }
             }
         }
@@ -617,22 +622,50 @@ __global__ void __launch_bounds__(NT, 2) projection_kernel(const ProjParams P)
             }
         }
         __syncthreads();
+        // pure background rows first: their loads are independent, so they all go out before the
+        // first store instead of paying one L2 round trip per row
+#pragma unroll
+        for (int k0 = 0; k0 < 8; k0 += 4) {        // up to 8 rows per warp and half, 4 in flight
+            uint4 bt[4];
+            uint2 bu[4];
+            bool bg[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int oy = oy_beg + warp + (k0 + k) * NW;
+                bg[k] = false;
+                if (oy < oy_end && lane < S / 8) {
+                    int y0; float t0, t1;
+                    lin_idx(oy, y0, t0, t1);
+                    const int y1 = y0 + (y0 < Q - 1 ? 1 : 0);
+                    bg[k] = y1 < ulo || y0 > uhi;
+                    if (bg[k]) {
+                        const int patch = (oy >> 4) * 14 + (lane >> 1);
+                        const int inner = (oy & 15) * 16 + (lane & 1) * 8;
+                        if (tile) bt[k] = __ldg(&tab->bg_tile[(patch * 256 + inner) >> 3]);
+                        if (u8) bu[k] = __ldg(&tab->bg_u8[(oy * S + 8 * lane) >> 3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int oy = oy_beg + warp + (k0 + k) * NW;
+                if (bg[k]) {
+                    const int patch = (oy >> 4) * 14 + (lane >> 1);
+                    const int inner = (oy & 15) * 16 + (lane & 1) * 8;
+                    if (tile) *reinterpret_cast<uint4 *>(tile + patch * 256 + inner) = bt[k];
+                    if (u8) *reinterpret_cast<uint2 *>(u8 + oy * S + 8 * lane) = bu[k];
+                }
+            }
+        }
         for (int oy = oy_beg + warp; oy < oy_end; oy += NW) {
-            const int y0 = __ldg(&tab->i0[oy]);
+            int y0; float lh0, lh1;
+            lin_idx(oy, y0, lh0, lh1);     // same arithmetic as the column table (bit-identical)
             const int y1 = y0 + (y0 < Q - 1 ? 1 : 0);
             if (lane >= S / 8) continue;
             const int g = lane;
             const int patch = (oy >> 4) * 14 + (g >> 1);
             const int inner = (oy & 15) * 16 + (g & 1) * 8;
-            if (y1 < ulo || y0 > uhi) {            // warp-uniform: pure background row
-                if (tile)
-                    *reinterpret_cast<uint4 *>(tile + patch * 256 + inner) =
-                        __ldg(&tab->bg_tile[(patch * 256 + inner) >> 3]);
-                if (u8)
-                    *reinterpret_cast<uint2 *>(u8 + oy * S + 8 * g) = __ldg(&tab->bg_u8[(oy * S + 8 * g) >> 3]);
-                continue;
-            }
-            const float lh0 = __ldg(&tab->l0[oy]), lh1 = __ldg(&tab->l1[oy]);
+            if (y1 < ulo || y0 > uhi) continue;    // warp-uniform: pure background row, done above
             const f32x2 h0 = pack2(lh0, lh0), h1 = pack2(lh1, lh1);
             const ulonglong2 *r0 = reinterpret_cast<const ulonglong2 *>(sm.G + (y0 - ybase) * S + 8 * g);
             const ulonglong2 *r1 = reinterpret_cast<const ulonglong2 *>(sm.G + (y1 - ybase) * S + 8 * g);
