@@ -25,7 +25,8 @@
  * Conventions
  *   - plain C, no torch types.  Every pointer named d_* is a DEVICE pointer supplied by the caller;
  *     the library owns no caller-visible tensors.  The handle owns only converted weights (bf16
- *     copies, folded patch-embed), TMA descriptors and the view table.
+ *     copies, folded patch-embed), the view / interpolation tables and the projection's point pool
+ *     (one 0.5 MB slot per CTA that can be resident, ~150 MB, allocated in vg_create).
  *   - all work is enqueued on the caller's stream (a cudaStream_t passed as void*); no internal
  *     synchronisation except in vg_create / vg_load_vit_weights / vg_set_text_features.
  *   - returns VG_OK (0) or a negative VgStatus; never throws.  vg_last_error gives the text.
