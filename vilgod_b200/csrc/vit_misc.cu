@@ -108,64 +108,108 @@ __global__ void __launch_bounds__(256) ln_pre_kernel(float *__restrict__ x,
     }
 }
 
-// One CTA (256 threads) per image: ln_post(CLS) -> @proj -> /|f| -> logit_scale * f.T^T -> softmax
+// One CTA (256 threads) per kHeadImgs images: ln_post(CLS) -> @proj -> /|f| -> logit_scale * f.T^T ->
+// softmax (model.py:236-239, clip_utils.py:41-43).  The 1.5 MB projection matrix and the text
+// features are streamed from L2 once per CTA and reused for all its images (one image per CTA made
+// the kernel L2-bandwidth bound); per image the arithmetic and its order are unchanged.
+constexpr int kHeadImgs = 8;
 __global__ void __launch_bounds__(256) head_kernel(const float *__restrict__ x,
                                                    const float *__restrict__ lw,
                                                    const float *__restrict__ lb,
                                                    const float *__restrict__ proj,
                                                    const float *__restrict__ text, int P,
-                                                   float logit_scale, float *__restrict__ probs,
+                                                   float logit_scale, int64_t B,
+                                                   float *__restrict__ probs,
                                                    int32_t *__restrict__ top1,
                                                    float *__restrict__ feats,
                                                    float *__restrict__ logits_out)
 {
-    __shared__ float sy[kWidth];
-    __shared__ float sf[kEmbed];
-    __shared__ float sred[8];
-    __shared__ float slog[kMaxPrompts];
+    constexpr int G = kHeadImgs;
+    __shared__ __align__(16) float sy[kWidth][G];     // ln_post(CLS), image index fastest
+    __shared__ float sf[G][kEmbed];
+    __shared__ float sred[G][8];
+    __shared__ float slog[G][kMaxPrompts];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t img = blockIdx.x;
-    if (warp == 0) {
+    const int64_t img0 = (int64_t)blockIdx.x * G;
+    const int nimg = (int)min((int64_t)G, B - img0);
+    {   // warp g normalises the class token of image g
         Row768 r;
-        r.load(x + img * (int64_t)kTokens * kWidth, lane);
-        r.normalise(lw, lb, lane);
+        if (warp < nimg) {
+            r.load(x + (img0 + warp) * (int64_t)kTokens * kWidth, lane);
+            r.normalise(lw, lb, lane);
+        } else {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) reinterpret_cast<float4 *>(sy)[lane + 32 * i] = r.v[i];
+            for (int i = 0; i < 6; ++i) r.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const int k = 4 * (lane + 32 * i);
+            sy[k + 0][warp] = r.v[i].x;
+            sy[k + 1][warp] = r.v[i].y;
+            sy[k + 2][warp] = r.v[i].z;
+            sy[k + 3][warp] = r.v[i].w;
+        }
     }
     __syncthreads();
-    float f0 = 0.0f, f1 = 0.0f;
-#pragma unroll 4
+    float f0[G], f1[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) { f0[g] = 0.0f; f1[g] = 0.0f; }
+#pragma unroll 2
     for (int k = 0; k < kWidth; ++k) {
-        const float yk = sy[k];
-        f0 = fmaf(yk, __ldg(proj + (size_t)k * kEmbed + tid), f0);
-        f1 = fmaf(yk, __ldg(proj + (size_t)k * kEmbed + tid + 256), f1);
-    }
-    float ss = warp_sum(f0 * f0 + f1 * f1);
-    if (lane == 0) sred[warp] = ss;
-    __syncthreads();
-    float tot = 0.0f;
+        const float p0 = __ldg(proj + (size_t)k * kEmbed + tid);
+        const float p1 = __ldg(proj + (size_t)k * kEmbed + tid + 256);
+        const float4 ya = *reinterpret_cast<const float4 *>(&sy[k][0]);
+        const float4 yb = *reinterpret_cast<const float4 *>(&sy[k][4]);
+        const float yk[G] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) tot += sred[i];
-    const float inv = 1.0f / sqrtf(tot);
-    f0 *= inv; f1 *= inv;
-    sf[tid] = f0; sf[tid + 256] = f1;
-    if (feats) {
-        feats[img * kEmbed + tid] = f0;
-        feats[img * kEmbed + tid + 256] = f1;
+        for (int g = 0; g < G; ++g) {
+            f0[g] = fmaf(yk[g], p0, f0[g]);
+            f1[g] = fmaf(yk[g], p1, f1[g]);
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const float ss = warp_sum(f0[g] * f0[g] + f1[g] * f1[g]);
+        if (lane == 0) sred[g][warp] = ss;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        float tot = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot += sred[g][i];
+        const float inv = 1.0f / sqrtf(tot);
+        const float a0 = f0[g] * inv, a1 = f1[g] * inv;
+        sf[g][tid] = a0; sf[g][tid + 256] = a1;
+        if (feats && g < nimg) {
+            feats[(img0 + g) * kEmbed + tid] = a0;
+            feats[(img0 + g) * kEmbed + tid + 256] = a1;
+        }
     }
     __syncthreads();
     for (int p = warp; p < P; p += 8) {
-        float d = 0.0f;
-        for (int e = lane; e < kEmbed; e += 32) d = fmaf(logit_scale * sf[e], __ldg(text + p * kEmbed + e), d);
-        d = warp_sum(d);
-        if (lane == 0) slog[p] = d;
+        float d[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) d[g] = 0.0f;
+        for (int e = lane; e < kEmbed; e += 32) {
+            const float t = __ldg(text + p * kEmbed + e);
+#pragma unroll
+            for (int g = 0; g < G; ++g) d[g] = fmaf(logit_scale * sf[g][e], t, d[g]);
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const float v = warp_sum(d[g]);
+            if (lane == 0) slog[g][p] = v;
+        }
     }
     __syncthreads();
-    if (warp == 0) {
+    if (warp < nimg) {      // warp g: soft-max and arg-max of image g
+        const int64_t img = img0 + warp;
+        const float *sl = slog[warp];
         float m = -INFINITY;
         int arg = 0;
         for (int p = lane; p < P; p += 32) {
-            const float v = slog[p];
+            const float v = sl[p];
             if (v > m) { m = v; arg = p; }
         }
 #pragma unroll
@@ -175,11 +219,11 @@ __global__ void __launch_bounds__(256) head_kernel(const float *__restrict__ x,
             if (om > m || (om == m && oa < arg)) { m = om; arg = oa; }
         }
         float s = 0.0f;
-        for (int p = lane; p < P; p += 32) s += expf(slog[p] - m);
+        for (int p = lane; p < P; p += 32) s += expf(sl[p] - m);
         s = warp_sum(s);
         for (int p = lane; p < P; p += 32) {
-            probs[img * P + p] = expf(slog[p] - m) / s;
-            if (logits_out) logits_out[img * P + p] = slog[p];
+            probs[img * P + p] = expf(sl[p] - m) / s;
+            if (logits_out) logits_out[img * P + p] = sl[p];
         }
         if (lane == 0) top1[img] = arg;
     }
@@ -355,9 +399,9 @@ int launch_head(VgHandle *h, const float *x, int64_t B, float *probs, int32_t *t
 {
     if (B <= 0) return VG_OK;
     VgProfScope prof(h, VG_K_HEAD, (double)B * kWidth * 4.0, st);
-    head_kernel<<<(unsigned)B, 256, 0, st>>>(x, h->vit.ln_post_w, h->vit.ln_post_b, h->vit.proj,
-                                             h->d_text, h->num_prompts, (float)h->cfg.logit_scale,
-                                             probs, top1, feats, logits);
+    head_kernel<<<(unsigned)((B + kHeadImgs - 1) / kHeadImgs), 256, 0, st>>>(
+        x, h->vit.ln_post_w, h->vit.ln_post_b, h->vit.proj, h->d_text, h->num_prompts,
+        (float)h->cfg.logit_scale, B, probs, top1, feats, logits);
     VG_LAUNCH_CHECK(h);
     return VG_OK;
 }
