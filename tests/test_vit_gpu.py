@@ -126,6 +126,27 @@ def test_tower_stages_against_reference_golden(golden, tag, operand_dtype):
         e.close()
 
 
+@pytest.mark.parametrize("switches", [("VG_LN_UNFUSED",), ("VG_GEMM_NARROW",), ("VG_ATTN_V1",),
+                                      ("VG_GEMM_V1", "VG_LN_UNFUSED")])
+def test_alternate_kernel_paths_stay_correct(golden, monkeypatch, switches):
+    """The A/B switches (read once in vg_create) select the unfused LayerNorm kernels, the 4-warp
+    residual epilogues, the mma.sync attention and the single-CTA GEMM: each must meet the same
+    stated tolerances against the reference as the production path."""
+    from vilgod_b200.engine import u8_to_tiles
+    g = golden["vit"]
+    for name in switches:
+        monkeypatch.setenv(name, "1")
+    e = _loaded_engine(golden, "ln", "bf16")
+    try:
+        tiles = u8_to_tiles(torch.from_numpy(g["u8"]).cuda(), e.op_torch_dtype)
+        res = e.encode_score(tiles, want_logits=True)
+        d = res["logits"].cpu().numpy() - g["ln_logits"]
+        assert np.abs(d).max() <= 0.15 and np.abs(d - d.mean(axis=1, keepdims=True)).max() <= 0.06
+        assert np.abs(res["probs"].cpu().numpy() - g["ln_probs"]).max() <= 0.01
+    finally:
+        e.close()
+
+
 def test_head_matches_oracle_given_same_residual(golden):
     """Isolate the fused head: feed the kernel's own block-11 residual stream to the oracle's
     ln_post / proj / normalise / score and compare at fp32 tolerance."""

@@ -67,7 +67,7 @@ int encode_chunk(VgHandle *h, const op_t *tiles, int64_t n, const EncodeBuffers 
     // residual-producing epilogues emit a bf16 copy of x plus per-row sum / sum of squares, the
     // QKV and c_fc GEMMs multiply the raw bf16 residual by gamma-scaled weights and normalise in
     // their epilogue.  VG_LN_UNFUSED=1 selects the separate LayerNorm kernels (A/B, debugging).
-    static const bool unfused = getenv("VG_LN_UNFUSED") != nullptr;
+    const bool unfused = h->sw.ln_unfused;
     if ((rc = launch_ln_pre(h, eb.x, n, unfused ? nullptr : eb.xb, unfused ? nullptr : eb.stats, st)))
         return rc;
     const int stop = dbg ? dbg->stop_after_layer : -1;
@@ -154,6 +154,12 @@ int vg_create(const VgConfig *cfg, VgHandle **out)
         delete h;
         return VG_ECUDA;
     }
+    h->sw.ln_unfused = getenv("VG_LN_UNFUSED") != nullptr;
+    h->sw.gemm_v1 = getenv("VG_GEMM_V1") != nullptr;
+    h->sw.gemm_narrow = getenv("VG_GEMM_NARROW") != nullptr;
+    h->sw.attn_v1 = getenv("VG_ATTN_V1") != nullptr;
+    if (getenv("VG_ATTN_TRACE") && cudaMalloc(&h->attn_trace, 16 * 8 * sizeof(long long)) != cudaSuccess)
+        h->attn_trace = nullptr;
     *out = h;
     return VG_OK;
 }
@@ -167,6 +173,7 @@ void vg_destroy(VgHandle *h)
     if (h->proj_spill_flags) cudaFree(h->proj_spill_flags);
     if (h->d_text) cudaFree(h->d_text);
     if (h->d_class_map) cudaFree(h->d_class_map);
+    if (h->attn_trace) cudaFree(h->attn_trace);
     for (auto &r : h->prof) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }
     for (auto e : h->event_pool) cudaEventDestroy(e);
     delete h;

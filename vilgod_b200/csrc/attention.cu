@@ -207,7 +207,7 @@ int launch_attention(VgHandle *h, const op_t *qkv_op, int64_t B, op_t *out_op,
 {
     if (B <= 0) return VG_OK;
     // production path: tcgen05 kernel (attention_tcgen05.cu); VG_ATTN_V1=1 selects this mma.sync one
-    static const bool force_v1 = getenv("VG_ATTN_V1") != nullptr && kOperandDtype == 0;   // mma.sync kernel is bf16 only
+    const bool force_v1 = h->sw.attn_v1 && kOperandDtype == 0;   // mma.sync kernel is bf16 only
     if (!force_v1) return launch_attention_tc(h, qkv_op, B, out_op, st);
     const __nv_bfloat16 *qkv = reinterpret_cast<const __nv_bfloat16 *>(qkv_op);
     __nv_bfloat16 *out = reinterpret_cast<__nv_bfloat16 *>(out_op);

@@ -433,8 +433,7 @@ int launch_attention_tc(VgHandle *h, const op_t *qkv, int64_t B, op_t *out,
     const int64_t items = B * kHeads;
     const int grid = (int)(items < h->num_sms ? items : h->num_sms);
     VgProfScope prof(h, VG_K_ATTENTION, 4.0 * (double)B * kHeads * L * L * HD, st);
-    static long long *trace = nullptr;
-    if (!trace && getenv("VG_ATTN_TRACE")) cudaMalloc(&trace, 16 * 8 * sizeof(long long));
+    long long *trace = h->attn_trace;
     attention_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(map, out, items, trace);
     if (trace) {
         long long hbuf[16 * 8];

@@ -98,9 +98,17 @@ struct VgHandle {
     size_t arena_bytes = 0;
     void *tma_encode = nullptr;     // cuTensorMapEncodeTiled entry point
     void *proj_tables = nullptr;    // bilinear tables + background tile (projection.cu)
-    void *proj_spill = nullptr;     // per-resident-CTA global depth grids for clusters > CAP points
+    void *proj_spill = nullptr;     // per-resident-CTA point pools for clusters > CAP points
     void *proj_spill_flags = nullptr;
     int proj_spill_sms = 0;
+    // A/B and debugging switches, read from the environment once in vg_create
+    struct {
+        bool ln_unfused = false;    // VG_LN_UNFUSED: separate LayerNorm kernels instead of the folded GEMMs
+        bool gemm_v1 = false;       // VG_GEMM_V1: single-CTA GEMM kernel
+        bool gemm_narrow = false;   // VG_GEMM_NARROW: 4-warp / 4-stage residual epilogues everywhere
+        bool attn_v1 = false;       // VG_ATTN_V1: mma.sync attention (bf16 build only)
+    } sw;
+    long long *attn_trace = nullptr;   // VG_ATTN_TRACE: clock64 stamps of CTA 0 (attention_tcgen05.cu)
 };
 
 #define VG_SET_ERR(h, ...)                                   \

@@ -295,7 +295,7 @@ int launch_gemm(VgHandle *h, const GemmArgs &g, cudaStream_t st)
     }
     // production path: 2-CTA kernel with TMA-store epilogues (gemm_tcgen05_2cta.cu).  The single-CTA
     // kernel below serves the patch embedding (row-remapping epilogue) and VG_GEMM_V1=1 (A/B runs).
-    static const bool force_v1 = getenv("VG_GEMM_V1") != nullptr;
+    const bool force_v1 = h->sw.gemm_v1;
     if (g.epilogue == kEpiPatch && !force_v1) return launch_gemm_patch_2cta(h, g, st);
     if (g.epilogue != kEpiPatch && !force_v1) return launch_gemm_2cta(h, g, st);
     if (g.stats) {

@@ -550,9 +550,9 @@ int launch_gemm_2cta(VgHandle *h, const GemmArgs &g, cudaStream_t st)
             return lnf ? launch_t<VG_EPI_BIAS_QGELU_BF16, true>(h, g, st)
                        : launch_t<VG_EPI_BIAS_QGELU_BF16, false>(h, g, st);
         case VG_EPI_BIAS_RESID_F32:
-            if (lnf && g.K <= kWidth && !getenv("VG_GEMM_NARROW"))   // out-proj: epilogue bound -> 8 warps
+            if (lnf && g.K <= kWidth && !h->sw.gemm_narrow)   // out-proj: epilogue bound -> 8 warps
                 return launch_t<VG_EPI_BIAS_RESID_F32, true, kWide>(h, g, st);
-            if (lnf && !getenv("VG_GEMM_NARROW"))                    // c_proj: tensor bound -> 5-stage ring
+            if (lnf && !h->sw.gemm_narrow)                    // c_proj: tensor bound -> 5-stage ring
                 return launch_t<VG_EPI_BIAS_RESID_F32, true, kDeep>(h, g, st);
             return lnf ? launch_t<VG_EPI_BIAS_RESID_F32, true>(h, g, st)
                        : launch_t<VG_EPI_BIAS_RESID_F32, false>(h, g, st);
