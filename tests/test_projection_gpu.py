@@ -171,6 +171,59 @@ def test_degenerate_and_edge_clusters(engines):
     assert out0["tiles"].shape[0] == 0
 
 
+def _adversarial_clusters():
+    rng = np.random.default_rng(99)
+    parts = []
+    plane = rng.uniform(-1, 1, size=(64, 3)); plane[:, 2] = 0.25                 # no extent in z
+    line = np.zeros((50, 3)); line[:, 0] = np.linspace(-2, 3, 50)                # extent in x only
+    two = np.array([[0.0, 0.0, 0.0], [1.0, 2.0, 3.0]])
+    tiny = 5.0 + 1e-6 * rng.uniform(-1, 1, size=(40, 3))                         # fp32 grains
+    far = 1e5 + rng.uniform(-0.5, 0.5, size=(200, 3))                            # large magnitude
+    lattice = np.stack(np.meshgrid(*[np.arange(8.0)] * 3, indexing="ij"), -1).reshape(-1, 3)   # cell edges
+    zcol = rng.normal(size=(300, 3)) * np.array([0.2, 0.2, 3.0])                 # z is the long axis
+    box = rng.uniform(-1, 1, size=(2000, 3)) * np.array([2.3, 0.9, 0.8])
+    shell = rng.normal(size=(5000, 3)); shell /= np.linalg.norm(shell, axis=1, keepdims=True)
+    for a in (plane, line, two, tiny, far, lattice, zcol, box, shell):
+        parts.append(np.asarray(a, np.float32))
+    off = np.zeros(len(parts) + 1, np.int32)
+    off[1:] = np.cumsum([len(a) for a in parts])
+    return np.concatenate(parts), off
+
+
+@pytest.mark.parametrize("depth_bias,obj_ratio", [(0.2, 0.8), (0.0, 0.8), (0.05, 1.0)])
+def test_adversarial_geometry_and_slice_ties(depth_bias, obj_ratio):
+    """Planar, linear, two-point, tiny, far-away, lattice-aligned and z-dominant clusters, under the
+    reference's normalisation constants and two others.  depth_bias = 0 puts points into depth slice 0,
+    whose value (1.0) ties with slice 1: the kernel's single-clear scheme has to notice and clear."""
+    from vilgod_b200 import _lib
+    from vilgod_b200.engine import Engine
+    pts, off = _adversarial_clusters()
+    V = 4
+    eng = Engine(num_views=V, rotate_mode=_lib.VG_ROTATE_FUSED, depth_bias=depth_bias, obj_ratio=obj_ratio)
+    try:
+        out = eng.project(pts, off, want_u8=True, want_densified=True, want_grid=True)
+        assert int(out["status"].abs().sum()) == 0
+        dens_o, u8_o = op.project_batch_threaded(pts, off, op.view_rot_mats(V), fused=True, want_dens=True,
+                                                 obj_ratio=obj_ratio, depth_bias=depth_bias)
+        assert np.array_equal(out["densified"].cpu().numpy().reshape(dens_o.shape), dens_o)
+        assert np.array_equal(out["u8"].cpu().numpy().reshape(u8_o.shape), u8_o)
+        assert torch.equal(tiles_to_u8(out["tiles"]), out["u8"])
+        # stage tap: the scatter-max grid of every (cluster, view) equals the oracle's points2grid
+        grid = out["grid"].cpu().numpy().reshape(len(off) - 1, V, 8, 112, 112)
+        rot = op.view_rot_mats(V)
+        occupied = set()
+        for c in (1, 5, 6):
+            for v in range(V):
+                q = op.rotate(pts[off[c]:off[c + 1]], rot[v], fused=True)
+                g_o = op.points2grid(q, obj_ratio=obj_ratio, depth_bias=depth_bias)
+                assert np.array_equal(grid[c, v], g_o.reshape(8, 112, 112)), (c, v)
+                occupied |= set(np.flatnonzero(g_o.reshape(8, -1).max(axis=1) > 0).tolist())
+        if depth_bias == 0.0:
+            assert 0 in occupied          # the tie path was really exercised
+    finally:
+        eng.close()
+
+
 def test_determinism_and_properties_at_scale(engines):
     """cfg2-sized slice (2 frames x ~300 clusters, 10 views): run-to-run bit stable (scatter-max is
     order independent); every image has background 255/254 only where untouched, and its minimum
