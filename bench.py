@@ -175,7 +175,7 @@ def run_reference_arm(a):
                              "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit_result(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -371,15 +371,32 @@ def run_ours(a):
             "images_per_second": C_all * V * a.steps / (ms_total * 1e-3),
             "kernel_breakdown_rank0": breakdown, "clocks": clocks, "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line), flush=True)
+        emit_result(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     eng.close()
 
 
+_RESULT_OUT = None
+
+
+def emit_result(line):
+    """The one JSON line of the contract, on the process's ORIGINAL stdout."""
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _RESULT_OUT
     a = parse_args()
+    # stdout must carry exactly one JSON line, but native libraries write there too (NCCL prints its
+    # "NCCL version ..." banner to fd 1): keep a private handle on the real stdout for the result and
+    # point fd 1 at stderr for everything else
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference_arm(a)
     else:
