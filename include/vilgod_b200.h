@@ -49,7 +49,7 @@ extern "C" {
 #define VG_API
 #endif
 
-#define VG_ABI_VERSION 1
+#define VG_ABI_VERSION 2
 #define VG_MAX_VIEWS 16
 #define VG_VIT_LAYERS 12
 #define VG_VIT_WIDTH 768
@@ -74,13 +74,22 @@ typedef struct VgHandle VgHandle;
 enum { VG_ROTATE_TORCH_CPU = 0, /* 9N < 400: ((x r0)+(y r1))+(z r2), else fma chain */
        VG_ROTATE_FUSED = 1, VG_ROTATE_UNFUSED = 2 };
 
+/* div_mode: how `/ (1 + depth_bias)` (mv_utils.py:112, a division by a Python scalar) is rounded.
+ * torch-CPU -- the reference path the oracle is pinned to -- does a true fp32 division; torch-CUDA
+ * multiplies by the fp32-rounded reciprocal, which differs in the last bit for ~22 % of inputs
+ * (hard part 1c).  Every other division on the path is by a tensor or by 2. */
+enum { VG_DIV_TRUE = 0, VG_DIV_RECIPROCAL = 1 };
+
 typedef struct VgConfig {
     int32_t abi_version;      /* VG_ABI_VERSION */
-    int32_t resolution;       /* R, reference 112 (tools/configs/preprocessor/waymo.yaml:79) */
+    int32_t resolution;       /* R: 112 (reference, tools/configs/preprocessor/waymo.yaml:79) or 224 */
     int32_t depth;            /* D, reference 8 */
     int32_t image_size;       /* S, reference 224 (tools/configs/preprocessing.yaml:78) */
     int32_t num_views;        /* V <= VG_MAX_VIEWS */
     int32_t rotate_mode;      /* VG_ROTATE_* */
+    int32_t div_mode;         /* VG_DIV_* */
+    int32_t pool_kernel;      /* GridToImage max-pool window, reference 5 (waymo.yaml:81-85) */
+    int32_t pool_pad;         /* its padding, reference 1; only (5, 1) is implemented */
     double obj_ratio;         /* 0.8  (python scalars: converted to fp32 like torch does) */
     double depth_bias;        /* 0.2 */
     double logit_scale;       /* 100.0 (src/utils/clip_utils.py:43) */
@@ -126,9 +135,10 @@ VG_API int vg_create(const VgConfig *cfg, VgHandle **out);
 VG_API void vg_destroy(VgHandle *h);
 VG_API const char *vg_last_error(const VgHandle *h);
 VG_API int vg_abi_version(void);
-/* GEMM operand type this build of the library computes in: 0 = bf16 (libvilgod_b200.so),
- * 1 = fp16 (libvilgod_b200_f16.so, the reference's own GPU dtype).  Every buffer documented as
- * "bf16" below holds that type.  Accumulation / residual stream / soft-max are fp32 in both. */
+/* GEMM operand type this build of the library computes in: 1 = fp16 (libvilgod_b200.so, the
+ * default: the reference's own GPU dtype, third_party/CLIP/clip/model.py:375-396), 0 = bf16
+ * (libvilgod_b200_bf16.so).  Every buffer documented as "bf16" / "operand type" below holds that
+ * type.  Accumulation / residual stream / soft-max are fp32 in both. */
 VG_API int vg_operand_dtype(void);
 
 VG_API int vg_load_vit_weights(VgHandle *h, const VgVitWeights *w, void *stream);
@@ -174,17 +184,32 @@ VG_API int vg_vote(VgHandle *h, const float *d_probs, const int32_t *d_top1, int
             int32_t *d_voted_class, float *d_voted_score, void *stream);
 
 /* project -> encode/score -> vote for C clusters, chunked internally to the workspace.
- * Outputs as above; d_tiles scratch comes out of the workspace. */
+ * Outputs as above; d_tiles scratch comes out of the workspace.
+ *   d_u8_first [C,224,224] uint8 (nullable): the first view's image of every cluster, which the
+ *   reference keeps as det.depth_image (zero_shot_detector.py:416-417, input_image_list[::V]). */
 VG_API int vg_classify(VgHandle *h, const float *d_points, const int32_t *d_offsets, int32_t C,
                 float *d_probs, int32_t *d_top1, float *d_feats, int32_t *d_voted_class,
-                float *d_voted_score, int32_t *d_status, void *d_ws, size_t ws_bytes,
-                void *stream);
+                float *d_voted_score, int32_t *d_status, uint8_t *d_u8_first, void *d_ws,
+                size_t ws_bytes, void *stream);
 
 /* ---- kernel-level test hooks (used by tests/ only; same kernels the entry points launch) ---- */
 enum { VG_EPI_BIAS_BF16 = 0, VG_EPI_BIAS_QGELU_BF16 = 1, VG_EPI_BIAS_RESID_F32 = 2 };
-/* out = epilogue(A[M,K] (bf16, row-major) x W[N,K]^T (bf16, row-major) + bias[N]) */
+/* out = epilogue(A[M,K] (operand type, row-major) x W[N,K]^T (row-major) + bias[N]) */
 VG_API int vg_test_gemm(VgHandle *h, const void *d_a, const void *d_w, const float *d_bias, int64_t M,
                  int32_t N, int32_t K, int32_t epilogue, void *d_out, void *stream);
+/* The LayerNorm-folded instantiations the tower runs (model.py:157-163,190-191), one launch:
+ *   VG_EPI_BIAS_BF16 / _QGELU_BF16: A is the RAW residual, d_stats [M,3,2] its per-row (sum, sum of
+ *     squares) slots, d_colsum [N]; out = epi(rstd_i (A W^T - mu_i colsum) + bias)   (QKV, c_fc)
+ *   VG_EPI_BIAS_RESID_F32 (N = 768): d_out fp32 [M,768] in/out residual; additionally writes the
+ *     operand-typed copy d_xb_out [M,768] and the row statistics d_stats [M,3,2] of the NEW
+ *     residual.  K <= 768 runs the out-proj instantiation, larger K the c_proj one. */
+VG_API int vg_test_gemm_lnf(VgHandle *h, const void *d_a, const void *d_w, const float *d_bias,
+                     const float *d_colsum, float *d_stats, void *d_xb_out, int64_t M, int32_t N,
+                     int32_t K, int32_t epilogue, void *d_out, void *stream);
+/* patch embedding on the production kernel: tiles [B,196,256] x w [768,256]^T + table [197,768]
+ * rows 1..196 -> x [B,197,768] rows 1..196 (row 0, the class token, is left untouched) */
+VG_API int vg_test_gemm_patch(VgHandle *h, const void *d_tiles, const void *d_w, const float *d_table,
+                       int64_t B, float *d_x, void *stream);
 /* qkv [B,197,2304] bf16 (q already scaled) -> out [B,197,768] bf16 */
 VG_API int vg_test_attention(VgHandle *h, const void *d_qkv, int64_t B, void *d_out, void *stream);
 /* x [rows,768] fp32 -> y bf16 [rows,768] = LayerNorm(x) * w + b */

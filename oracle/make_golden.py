@@ -122,6 +122,35 @@ def golden_projection():
     return out
 
 
+def golden_projection224():
+    """BASELINE.json configs[3] sweeps R in {112, 224}: the reference is parametric in `resolution`
+    (src/utils/mv_utils.py:91-127), so the same loop at R = 224 gives 222x222 densified images."""
+    from src.utils import mv_utils
+    pts, off = _special_clusters()
+    pick = [1, 5, 8, 11]                      # 17, 100, 2048 points and the cell-edge lattice
+    clusters = [pts[off[c]:off[c + 1]] for c in pick]
+    off2 = np.zeros(len(pick) + 1, dtype=np.int32)
+    off2[1:] = np.cumsum([len(c) for c in clusters])
+    V = 4
+    proj = rh.make_reference_projection(V, resolution=224)
+    cells, vals = [], []
+    for p in clusters:
+        t = torch.from_numpy(p)[None]
+        rp = proj.point_transform(torch.repeat_interleave(t, V, dim=0), proj.rot_mat.repeat(1, 1, 1))
+        grid = mv_utils.points2grid(rp.clone(), proj.resolution, proj.depth, proj.obj_ratio,
+                                    proj.depth_bias).squeeze()
+        g = grid.permute(0, 1, 3, 2).contiguous().numpy()
+        nz = np.flatnonzero(g)
+        cells.append(nz.astype(np.int32))
+        vals.append(g.reshape(-1)[nz])
+    res = rh.reference_classification(proj, None, clusters)
+    dens = np.ascontiguousarray(res["densified"].reshape(len(pick), V, 222, 222).transpose(0, 1, 3, 2))
+    _save("projection224.npz", points=np.concatenate(clusters), offsets=off2,
+          grid_cells=np.concatenate(cells), grid_vals=np.concatenate(vals),
+          grid_counts=np.asarray([len(c) for c in cells], dtype=np.int32),
+          u8=res["u8"].reshape(len(pick), V, 224, 224), dens_c1=dens[1], dens_c2v0=dens[2, 0])
+
+
 def golden_vit(clip_plain, clip_ln, u8_images):
     """8 depth images through the reference preprocess + encode_image + scoring, for the plain
     random-init checkpoint and for one whose LayerNorm weights/biases were perturbed."""
@@ -148,6 +177,12 @@ def golden_vit(clip_plain, clip_ln, u8_images):
         out[f"{tag}_ln_pre"] = stages["ln_pre"][:, :3, :].numpy()                  # [B,3 tok,768]
         out[f"{tag}_block0"] = stages["block0"].permute(1, 0, 2)[:, :3, :].numpy()   # LND -> NLD
         out[f"{tag}_block11"] = stages["block11"].permute(1, 0, 2)[:, :3, :].numpy()
+        if tag == "ln":
+            # every token of the first four images (fp16-compressed: 2^-11 relative, far below the
+            # stated tolerances): a wrong row statistic or a ragged-tile bug at tokens 3..196 must
+            # not hide behind the three rows above
+            out["ln_block0_full"] = stages["block0"].permute(1, 0, 2)[:4].numpy().astype(np.float16)
+            out["ln_block11_full"] = stages["block11"].permute(1, 0, 2)[:4].numpy().astype(np.float16)
         out[f"{tag}_feats"] = feats.numpy()
         out[f"{tag}_logits"] = logits.numpy()
         out[f"{tag}_probs"] = logits.softmax(dim=-1).numpy()
@@ -205,11 +240,12 @@ def golden_vote():
     _save("vote.npz", **out)
 
 
-def golden_e2e(clipw, num_clusters=128, V=6):
+def golden_e2e(clipw, num_clusters=128, V=6, name="e2e.npz", seed=None):
     """BASELINE.json configs[0]: one synthetic Waymo-shaped frame, 128 clusters <= 2048 points,
-    6 views, fp32 CLIP on CPU, exactly the loop of zero_shot_detector.py:389-416."""
+    6 views, fp32 CLIP on CPU, exactly the loop of zero_shot_detector.py:389-416.  With V = 10 and
+    another seed: a slice of configs[1] (the benchmarked workload)."""
     from vilgod_b200 import synthetic
-    pts, off = synthetic.make_clusters(num_clusters, seed=synthetic.DEFAULT_SEED)
+    pts, off = synthetic.make_clusters(num_clusters, seed=synthetic.DEFAULT_SEED if seed is None else seed)
     proj = rh.make_reference_projection(V)
     t = time.time()
     res = rh.reference_classification(proj, clipw, [pts[off[c]:off[c + 1]]
@@ -233,7 +269,7 @@ def golden_e2e(clipw, num_clusters=128, V=6):
             probs.append(torch.cat([(100.0 * f @ clipw.text_features.T), f], dim=1))
         pf = torch.cat(probs).numpy()
     import zlib
-    _save("e2e.npz", points=pts, offsets=off,
+    _save(name, points=pts, offsets=off,
           u8_crc32=np.asarray([zlib.crc32(a.tobytes()) for a in res["u8"]], dtype=np.uint32),
           u8_sum=res["u8"].reshape(len(res["u8"]), -1).sum(axis=1).astype(np.uint32),
           u8_first8=res["u8"][:8], logits=pf[:, :24], feats=pf[:, 24:].astype(np.float16),
@@ -273,8 +309,12 @@ def main():
         golden_vit(clip_plain, clip_ln, np.ascontiguousarray(u8))
     if want("vote"):
         print("vote ..."); golden_vote()
+    if want("projection224"):
+        print("projection224 ..."); golden_projection224()
     if want("e2e"):
         print("e2e ..."); golden_e2e(clip_plain)
+    if want("e2e_cfg2"):
+        print("e2e_cfg2 ..."); golden_e2e(clip_plain, num_clusters=96, V=10, name="e2e_cfg2.npz", seed=77)
 
 
 if __name__ == "__main__":

@@ -47,11 +47,19 @@ def lib():
         L.vgo_project_batch.argtypes = [fp, i32p, ctypes.c_int, fp, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                         ctypes.c_double, fp, ctypes.c_int, fp, u8p]
+        L.vgo_set_div_mode.argtypes = [ctypes.c_int]
+        L.vgo_set_div_mode.restype = None
         for f in (L.vgo_rotate, L.vgo_points2grid, L.vgo_densify, L.vgo_upsample_u8,
                   L.vgo_project_batch):
             f.restype = ctypes.c_int
         _lib = L
     return _lib
+
+
+def set_div_mode(mode):
+    """0: true division by (1 + depth_bias) (torch-CPU, the pinned reference behaviour);
+    1: multiplication by the fp32 reciprocal (torch-CUDA's scalar division).  Process-wide."""
+    lib().vgo_set_div_mode(int(mode))
 
 
 def _f(a):

@@ -64,6 +64,12 @@ int vgo_rotate(const float *pts, int64_t n, const float *rot9, int fused, float 
 /* mv_utils.py:99-127.  q: rotated points of ONE (cluster, view) [n,3].  grid: [D,R,R] as
  * (z_int, y, x), zero initialised here.  Also returns the per-point cell index and value when the
  * pointers are non-NULL (used by the stage-isolated parity tests). */
+static int vgo_div_mode = 0;   /* 0: true division (torch-CPU, pinned by the golden vectors);
+                                * 1: multiply by the fp32-rounded reciprocal, the way torch-CUDA
+                                *    evaluates a division by a Python scalar (SURVEY.md section 7,
+                                *    hard part 1c) -- UNPINNED: no CUDA run of the reference exists */
+void vgo_set_div_mode(int mode) { vgo_div_mode = mode; }
+
 int vgo_points2grid(const float *q, int64_t n, int R, int D, double obj_ratio_d,
                     double depth_bias_d, float *grid, int64_t *cell_out, float *val_out)
 {
@@ -105,7 +111,13 @@ int vgo_points2grid(const float *q, int64_t n, int R, int D, double obj_ratio_d,
         u[1] = u[1] * obj_ratio;
         float fx = u[0] + 1.0f; fx = fx / 2.0f; fx = fx * Rf;
         float fy = u[1] + 1.0f; fy = fy / 2.0f; fy = fy * Rf;
-        float fz = u[2] + 1.0f; fz = fz / 2.0f; fz = fz + depth_bias; fz = fz / one_plus_bias;
+        float fz = u[2] + 1.0f; fz = fz / 2.0f; fz = fz + depth_bias;
+        if (vgo_div_mode) {
+            float inv = 1.0f / one_plus_bias;
+            fz = fz * inv;
+        } else {
+            fz = fz / one_plus_bias;
+        }
         fz = fz * dm2;
         float X = ceilf(fx), Y = ceilf(fy), Zi = ceilf(fz);
         X = X < 1.0f ? 1.0f : (X > xy_hi ? xy_hi : X);

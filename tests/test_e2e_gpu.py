@@ -1,6 +1,11 @@
 """GPU end to end: BASELINE.json configs[0] (one synthetic Waymo-shaped frame, 128 clusters, 6
-views) through vg_classify against the golden run of the UNMODIFIED reference on the same inputs
-and random-init weights, plus a well-separated-prompt variant where top-1 must agree >= 99.5 %."""
+views) and a slice of configs[1] (96 clusters, 10 views) through vg_classify against the golden run
+of the UNMODIFIED reference on the same inputs and random-init weights.
+
+north_star's parity bar -- logits within the stated tolerance and >= 99.5 % top-1 agreement -- is
+asserted RAW (no margin filter) for the default build (fp16 operands, the one bench.py times), as
+24-way per-view, 4-class per-view and 4-class voted agreement.  The bf16-operand alternative build is
+held to its own, looser numbers (98.7 % raw on the collapsed random-init prompts) and says so."""
 import numpy as np
 import pytest
 import torch
@@ -12,7 +17,16 @@ from oracle import vote as ovote
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["bf16", "f16"])
+def agreement(engine, out, ref_logits, C, V, ref_voted):
+    """-> (24-way per-view, 4-class per-view, 4-class voted) raw agreement with the reference."""
+    top1 = out["top1"].cpu().numpy().reshape(-1)
+    ref_top1 = ref_logits.argmax(axis=1)
+    cmap = np.asarray(engine.class_map)
+    voted = np.asarray(engine.mapped_names)[out["voted_class"].cpu().numpy()]
+    return ((top1 == ref_top1).mean(), (cmap[top1] == cmap[ref_top1]).mean(), (voted == ref_voted).mean())
+
+
+@pytest.fixture(scope="module", params=["f16", "bf16"])
 def engine6(request):
     from vilgod_b200 import weights
     from vilgod_b200.engine import Engine
@@ -48,10 +62,46 @@ def test_cfg1_frame_against_reference_golden(golden, engine6):
     clear = margin > 0.06
     raw = (top1 == ref_top1).mean()
     aware = (top1[clear] == ref_top1[clear]).mean() if clear.any() else 1.0
+    a24, a4, avote = agreement(e, out, ref_logits, C, V, g["voted_name"])
     print(f"cfg1 [{e.operand_dtype}] top-1 agreement raw {raw:.4f}, margin-aware {aware:.4f} on "
-          f"{clear.sum()} images; max |dprob| {np.abs(probs - ref_probs).max():.5f}")
+          f"{clear.sum()} images; 4-class per-view {a4:.4f}, voted {avote:.4f}; "
+          f"max |dprob| {np.abs(probs - ref_probs).max():.5f}")
     assert aware >= 0.995
-    assert raw >= (0.80 if e.operand_dtype == "bf16" else 0.99)
+    if e.operand_dtype == "f16":     # the benchmarked build: north_star's bar, raw
+        assert a24 >= 0.995 and a4 >= 0.995 and avote >= 0.995, (a24, a4, avote)
+        d = out["probs"].cpu().numpy().reshape(C * V, 24)
+        assert np.abs(d - ref_probs).max() <= 0.002
+    else:                            # bf16 alternative: 8-bit mantissas against margins of ~0.05
+        assert a24 >= 0.97 and a4 >= 0.97 and avote >= 0.97, (a24, a4, avote)
+
+
+def test_cfg2_slice_against_reference_golden(golden):
+    """96 clusters x 10 views drawn like the benchmarked workload (BASELINE.json configs[1]), scored
+    by the unmodified reference: raw agreement of the default build, all three ways."""
+    from vilgod_b200 import weights
+    from vilgod_b200.engine import Engine
+    g, t = golden["e2e_cfg2"], golden["tables"]
+    C, V = 96, 10
+    for dt, bar in (("f16", 0.995), ("bf16", 0.97)):
+        e = Engine(num_views=V, operand_dtype=dt)
+        try:
+            e.load_vit_weights(weights.random_init_visual_state_dict(1234))
+            e.set_text_features(t["text_features"])
+            out = e.classify(g["points"], g["offsets"])
+            torch.cuda.synchronize()
+            assert int(out["status"].abs().sum()) == 0
+            a24, a4, avote = agreement(e, out, g["logits"], C, V, g["voted_name"])
+            ref_probs = torch.from_numpy(g["logits"]).softmax(dim=-1).numpy()
+            dp = np.abs(out["probs"].cpu().numpy().reshape(C * V, 24) - ref_probs).max()
+            names = np.asarray(e.class_list)[out["top1"].cpu().numpy()]
+            print(f"cfg2 slice [{dt}]: 24-way {a24:.4f}, 4-class {a4:.4f}, voted {avote:.4f}, max |dprob| {dp:.5f}")
+            assert min(a24, a4, avote) >= bar, (dt, a24, a4, avote)
+            assert dp <= (0.002 if dt == "f16" else 0.01)
+            assert (names == g["names"]).mean() >= bar
+            same = np.asarray(e.mapped_names)[out["voted_class"].cpu().numpy()] == g["voted_name"]
+            assert np.abs(out["voted_score"].cpu().numpy()[same] - g["voted_score"][same]).max() <= 0.01
+        finally:
+            e.close()
 
 
 def test_cfg1_frame_well_separated_prompts(golden, engine6):
@@ -81,7 +131,7 @@ def test_cfg1_frame_well_separated_prompts(golden, engine6):
     print(f"separated prompts [{e.operand_dtype}]: top-1 agreement raw {raw:.4f}, margin-aware {aware:.4f} on "
           f"{clear.sum()}/{len(clear)} images, median margin {np.median(margin):.3f}")
     assert clear.mean() > 0.5 and aware >= 0.995
-    assert raw >= 0.90
+    assert raw >= (0.995 if e.operand_dtype == "f16" else 0.90)
     assert np.abs(out["probs"].cpu().numpy() - ref["probs"]).max() <= 0.02
     names = np.asarray(e.mapped_names)[out["voted_class"].cpu().numpy()]
     # the 4-class voted label the loop consumes: exact wherever every view of the cluster is
@@ -90,7 +140,7 @@ def test_cfg1_frame_well_separated_prompts(golden, engine6):
     same = names == ref["voted_name"]
     print(f"voted labels: raw agreement {same.mean():.4f}, {cl.sum()} fully decidable clusters")
     assert same[cl].all()
-    assert same.mean() >= 0.85
+    assert same.mean() >= (0.995 if e.operand_dtype == "f16" else 0.85)
     # propagate_labels thresholds the voted score at 0.5 / 0.35 / 0.3
     # (zero_shot_detector.py:775-795) -- the only place small probability differences can change
     # pseudo-labels.  Same decision wherever the labels agree and the oracle score is not within the
@@ -176,3 +226,157 @@ def test_classify_is_cuda_graph_capturable(golden, engine6):
     torch.cuda.synchronize()
     assert torch.equal(out["top1"], eager["top1"])
     assert torch.equal(out["probs"], eager["probs"])
+
+
+class _StandInDetection:
+    """What the write-back touches on src/dataclass/objects.py:Detection (add_object_entry :105-111,
+    serialize :87-103, sync :113-118), without the reference tree (absent on the GPU box)."""
+    PARAMS = ['cluster_id', 'valid', 'object_class_predictions', 'object_class_predictions_detailed',
+              'object_class_predictions_score', 'object_class', 'object_class_score']
+
+    def __init__(self, cluster_id, points, gt=False):
+        self.cluster_id, self.cluster_points, self.gt, self.valid = cluster_id, points, gt, True
+        self.depth_image = None
+        for k in self.PARAMS[2:]:
+            setattr(self, k, None)
+
+    def add_object_entry(self, entry_name, key, data):
+        if getattr(self, entry_name) is None:
+            setattr(self, entry_name, {})
+        getattr(self, entry_name)[key] = data
+
+    @property
+    def serialize(self):
+        return {p: getattr(self, p) for p in self.PARAMS if getattr(self, p) is not None}
+
+    def sync_detection(self, data):
+        for k, v in data.items():
+            setattr(self, k, v)
+
+
+class _StandInFrame:
+    def __init__(self, dets, T):
+        self.detections, self.transform_to_ego = dets, T
+
+    def update_object_classes(self, *a, **k):
+        from vilgod_b200 import voting
+        voting.update_object_classes(self.detections, *a, **k)
+
+
+def _already_classified(frames, key_):
+    """The resume check at the top of classification(), zero_shot_detector.py:345-356."""
+    for fr in frames:
+        for det in fr.detections:
+            if det.object_class is not None and key_ in det.object_class:
+                return True
+    return False
+
+
+def test_frame_write_back_pickle_and_resume_on_gpu_output(golden, engine6):
+    """SURVEY.md section 8 row f3 on REAL GPU output: classify_lidar_frame (filter + fused call +
+    update_object_classes incl. depth images) -> Detection.serialize -> pickle -> sync into fresh
+    detections -> the 'already done?' check that lets classification() skip a finished sequence."""
+    import pickle
+    from vilgod_b200 import synthetic
+    from vilgod_b200.reference_api import classify_lidar_frame
+    e = engine6
+    e.set_text_features(golden["tables"]["text_features"])
+    key_ = "clip_a_point_representation_of_a"
+    raw, off, _ = synthetic.make_clusters_raw(14, n_min=10, n_max=700, seed=31)
+    T = np.eye(4); T[:3, 3] = [0.5, -1.0, 0.2]
+
+    def make_frames():
+        dets = [_StandInDetection(i, raw[off[i]:off[i + 1]], gt=(i in (3, 9))) for i in range(14)]
+        return [_StandInFrame(dets[:8], T), _StandInFrame(dets[8:], T), _StandInFrame([], T)]
+
+    frames = make_frames()
+    assert not _already_classified(frames, key_)
+    total = 0
+    for fr in frames:
+        upd = [True] * len(fr.detections)
+        total += classify_lidar_frame(e, fr, fr.detections, upd, key_)
+        # ground-truth detections are skipped (classify_gt is False in the reference) and flagged so
+        assert upd == [not d.gt for d in fr.detections]
+    assert total == 12
+    V = e.num_views
+    for fr in frames:
+        for d in fr.detections:
+            if d.gt:
+                assert d.object_class is None and d.depth_image is None
+                continue
+            assert d.object_class[key_] in e.mapped_names
+            assert isinstance(d.object_class[key_], str) and np.asarray(d.object_class_score[key_]).dtype == np.float32
+            assert d.object_class_predictions[key_].shape == (V,)
+            assert d.object_class_predictions_score[key_].dtype == np.float32
+            assert set(d.object_class_predictions_detailed[key_]) <= set(e.class_list)
+            assert d.depth_image.size == (224, 224) and d.depth_image.mode == "RGB"
+    # the depth image is the first view's projection of that cluster, bit for bit
+    from vilgod_b200 import canonicalise
+    c = 5
+    pk = canonicalise.canonicalise_packed(raw[off[c]:off[c + 1]], np.array([0, off[c + 1] - off[c]]), T)
+    u8 = e.project(pk, np.array([0, len(pk)], np.int32), want_tiles=False, want_u8=True)["u8"][0].cpu().numpy()
+    assert np.array_equal(np.asarray(frames[0].detections[c].depth_image)[..., 0], u8)
+    # sequence pickle round trip (sync_lidar_frames, zero_shot_detector.py:105-123) and resume
+    blob = pickle.dumps([[d.serialize for d in fr.detections] for fr in frames])
+    fresh = make_frames()
+    for fr, data in zip(fresh, pickle.loads(blob)):
+        for d, dd in zip(fr.detections, data):
+            d.sync_detection(dd)
+    assert _already_classified(fresh, key_)
+    for a, b in zip(fresh[1].detections, frames[1].detections):
+        if b.gt:
+            continue
+        assert a.object_class[key_] == b.object_class[key_]
+        assert np.array_equal(a.object_class_predictions_score[key_], b.object_class_predictions_score[key_])
+
+
+def test_empty_frames_empty_clusters_and_top_k(golden, engine6):
+    """Frames without clusters return empty arrays (the reference skips them), clusters without points
+    come back flagged instead of crashing the loop, and top_k > 1 (clip_utils.py:51-61) yields
+    (C, V * k) arrays, best first."""
+    from vilgod_b200 import synthetic
+    from vilgod_b200.reference_api import classify_frame
+    e = engine6
+    e.set_text_features(golden["tables"]["text_features"])
+    assert classify_frame(e, [])["class_names"].shape == (0, 6)
+    raw, off, _ = synthetic.make_clusters_raw(4, n_min=10, n_max=200, seed=2)
+    clusters = [raw[off[0]:off[1]], np.zeros((0, 3), np.float32), raw[off[1]:off[2]], raw[off[2]:off[3]]]
+    res = classify_frame(e, clusters, np.eye(4), want_depth_images=True)
+    assert list(res["status"]) == [0, -4, 0, 0] and res["class_names"].shape == (4, 6)
+    ref = classify_frame(e, [clusters[0], clusters[2], clusters[3]], np.eye(4))
+    assert np.array_equal(res["class_scores"][[0, 2, 3]], ref["class_scores"])
+    assert len(res["depth_images"]) == 4
+    k3 = classify_frame(e, [clusters[0], clusters[2]], np.eye(4), top_k=3)
+    assert k3["class_names"].shape == (2, 18) and k3["class_scores"].dtype == np.float32
+    s = k3["class_scores"].reshape(2, 6, 3)
+    assert (np.diff(s, axis=2) <= 0).all()                        # best first within every view
+    assert np.array_equal(s[:, :, 0], ref["class_scores"][[0, 1]])
+    # bad offsets are rejected on the host before the kernel can read out of bounds
+    with pytest.raises(ValueError):
+        e.classify(np.zeros((10, 3), np.float32), np.array([0, 20], np.int32))
+    with pytest.raises(ValueError):
+        e.classify(np.zeros((10, 3), np.float32), np.array([0, 5, 10], np.int32),
+                   out=e.alloc_outputs(1))
+
+
+def test_clip_wrapper_mirror_with_cached_features(golden):
+    """predict_clip_labels on PIL images (the reference's own intermediate) equals the golden run's
+    names for top_k = 1; the literal ClipWrapper(clip_cfg, model_path, device) constructor is
+    covered on the CPU (tests/test_host_side.py) because it needs the caller's `clip` package."""
+    from PIL import Image
+    from vilgod_b200 import weights
+    from vilgod_b200.reference_api import ClipWrapper
+    g, t = golden["vit"], golden["tables"]
+    cw = ClipWrapper(dict(top_k=1, split_size=50), None, device="cuda", text_features=t["text_features"],
+                     visual_state_dict=weights.random_init_visual_state_dict(1234), num_views=6)
+    try:
+        pil = [Image.fromarray(np.repeat(a[..., None], 3, axis=2)) for a in g["u8"]]
+        names, scores = cw.predict_clip_labels(pil)
+        assert len(names) == len(scores) == 8 and scores[0].dtype == np.float32
+        assert np.abs(np.asarray(scores) - g["plain_scores"]).max() <= 0.002
+        srt = np.sort(g["plain_logits"], axis=1)
+        clear = (srt[:, -1] - srt[:, -2]) > 0.01
+        assert (np.asarray(names)[clear] == g["plain_names"][clear]).all()
+        assert cw.predict_clip_labels([]) == ([], [])
+    finally:
+        cw.engine.close()

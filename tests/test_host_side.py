@@ -84,3 +84,74 @@ def test_synthetic_generator_is_deterministic_and_shaped(golden):
     assert off[-1] == len(pts) and bounds[-1] == len(off) - 1
     assert np.array_equal(pts[off[bounds[1]]:off[bounds[1] + 1]],
                           frames[1][0][frames[1][1][0]:frames[1][1][1]])
+
+
+def test_canonicalise_passes_empty_clusters_through():
+    """A cluster without points contributes nothing to the packed batch (the projection then
+    reports VG_EDEGENERATE for it); the reference guards only empty FRAMES
+    (zero_shot_detector.py:403)."""
+    raw, off, _ = synthetic.make_clusters_raw(5, n_min=10, n_max=50, seed=2)
+    ref = canonicalise.canonicalise_packed(raw, off)
+    off2 = np.array([0, 0, off[1], off[2], off[2], off[3], off[4], off[5], off[5]])
+    assert np.array_equal(canonicalise.canonicalise_packed(raw, off2), ref)
+    assert canonicalise.canonicalise_packed(np.zeros((0, 3)), np.array([0, 0])).shape == (0, 3)
+    with pytest.raises(ValueError):
+        canonicalise.canonicalise_packed(raw, np.array([0, 5, 3]))
+
+
+def test_classify_frame_on_a_frame_without_clusters():
+    """No engine call is made for an empty frame, so this runs without a GPU."""
+    from vilgod_b200.reference_api import classify_frame
+
+    class _NoEngine:
+        num_views = 6
+
+    res = classify_frame(_NoEngine(), [], np.eye(4))
+    assert res["class_names"].shape == (0, 6) and res["class_scores"].dtype == np.float32
+    assert res["voted_names"].shape == (0,) and res["depth_images"] == []
+
+
+def test_top_k_labels_follow_the_reference_tail():
+    """Same lists as clip_utils.py:49-63 builds from a probability matrix, for k = 1 and k = 3."""
+    from vilgod_b200.engine import CLASS_LIST
+    from vilgod_b200.reference_api import top_k_labels
+    rng = np.random.default_rng(4)
+    logits = rng.normal(size=(7, 24)).astype(np.float32)
+    probs = torch.from_numpy(logits).softmax(dim=-1).numpy()
+    ids = dict(enumerate(CLASS_LIST))
+    for k in (1, 3):
+        names, scores = top_k_labels(probs, k, ids)
+        assert len(names) == len(scores) == 7 * k
+        for i in range(7):
+            order = np.argsort(-probs[i])[:k]
+            assert names[i * k:(i + 1) * k] == [CLASS_LIST[j] for j in order]
+            assert np.array_equal(np.asarray(scores[i * k:(i + 1) * k]), probs[i][order])
+            assert scores[i * k].dtype == np.float32
+
+
+def test_prompt_encoding_through_the_callers_clip_package(golden, tmp_path):
+    """ClipWrapper(clip_cfg, model_path, device) builds text_features itself, through the caller's
+    `clip` (clip_utils.py:19-26).  With the reference tree mounted, the helper must reproduce the
+    reference wrapper's text features and hand over the visual weights the reference model holds."""
+    from oracle import ref_harness as rh
+    if not rh.available():
+        pytest.skip("reference tree not mounted")
+    rh.install_shims()
+    from vilgod_b200.reference_api import encode_prompts_with_clip
+    rh.make_random_checkpoint(str(tmp_path / "ViT-B-16.pt"), seed=1234)
+    orig = torch.jit.load
+
+    def _no_jit(*a, **k):      # SURVEY.md 8c: clip.load's JIT attempt consumes the file handle on torch 2.11
+        raise RuntimeError("not a JIT archive (shim)")
+
+    torch.jit.load = _no_jit
+    try:
+        model, preprocess, tok, tf = encode_prompts_with_clip(rh.clip_cfg(), str(tmp_path), "cpu")
+    finally:
+        torch.jit.load = orig
+    g = golden["tables"]
+    assert np.array_equal(tok[0].numpy(), g["text_tokens0"])
+    assert np.array_equal(tf.detach().float().numpy(), g["text_features"])
+    from oracle.make_golden import weights_fingerprint
+    sha, _ = weights_fingerprint({k: v.float() for k, v in model.visual.state_dict().items()})
+    assert sha == str(golden["vit"]["plain_weights_sha256"])

@@ -64,6 +64,49 @@ def test_projection_end_to_end(golden, V):
     assert mism.mean() < 3e-3, mism.mean()
 
 
+def test_projection_r224_against_reference(golden):
+    """BASELINE.json configs[3] sweeps the grid resolution: the oracle at R = 224 against the
+    reference's own run at resolution 224 (222x222 densified images)."""
+    g = golden["projection224"]
+    pts, off, V = g["points"], g["offsets"], 4
+    rot = op.view_rot_mats(V)
+    cells, vals, counts = g["grid_cells"], g["grid_vals"], g["grid_counts"]
+    pos = 0
+    for c in range(len(off) - 1):
+        p = pts[off[c]:off[c + 1]]
+        fused = 9 * len(p) >= 400
+        grid = np.stack([op.points2grid(op.rotate(p, rot[v], fused=fused), R=224) for v in range(V)])
+        nz = np.flatnonzero(grid)
+        assert np.array_equal(nz, cells[pos:pos + counts[c]])
+        assert np.array_equal(grid.reshape(-1)[nz], vals[pos:pos + counts[c]])
+        pos += counts[c]
+        d, u = op.project_batch(p, np.array([0, len(p)], np.int32), rot, R=224, fused=fused)
+        if c == 1:
+            assert np.abs(d[0] - g["dens_c1"]).max() <= 1e-5
+        if c == 2:
+            assert np.abs(d[0, 0] - g["dens_c2v0"]).max() <= 1e-5
+        assert np.abs(u[0].astype(int) - g["u8"][c].astype(int)).max() <= 1
+        assert (u[0] != g["u8"][c]).mean() < 3e-3
+
+
+def test_reciprocal_div_mode_differs_only_in_the_last_bit(golden):
+    """div_mode 1 restates torch-CUDA's scalar division (x * fp32(1/1.2)): the quotient moves by at
+    most one ulp (two after the following `* (depth - 2)`), a cell changes only where that crosses a
+    ceil() boundary."""
+    g = golden["projection"]
+    off = g["offsets"]
+    q = g["rotated4"].reshape(-1, 4, 3)[off[8]:off[9], 1]          # 2048 points
+    try:
+        g0, c0, v0 = op.points2grid(q, return_cells=True)
+        op.set_div_mode(1)
+        g1, c1, v1 = op.points2grid(q, return_cells=True)
+    finally:
+        op.set_div_mode(0)
+    assert (c0 != c1).mean() < 1e-3
+    ulp = np.abs(v0.view(np.int32).astype(np.int64) - v1.view(np.int32).astype(np.int64))
+    assert ulp.max() <= 2 and 0.05 < (ulp > 0).mean() < 0.5
+
+
 def test_upsample_u8_bit_exact_on_reference_images(golden):
     g = golden["projection"]
     for c in (0, 5, 9):
@@ -110,6 +153,10 @@ def test_vit_oracle_matches_reference(golden, tag):
     assert np.abs(st["ln_pre"][:, :3].numpy() - g[f"{tag}_ln_pre"]).max() < 2e-5
     assert np.abs(st["block0"][:, :3].numpy() - g[f"{tag}_block0"]).max() < 5e-5
     assert np.abs(st["block11"][:, :3].numpy() - g[f"{tag}_block11"]).max() < 5e-4
+    if tag == "ln":      # every token of four images (golden stored as fp16: 2^-11 relative)
+        for name in ("block0", "block11"):
+            ref = g[f"ln_{name}_full"].astype(np.float32)
+            assert np.abs(st[name][:4].numpy() - ref).max() <= 2.0 ** -11 * np.abs(ref).max() + 5e-4
     assert np.abs(feats.numpy() - g[f"{tag}_feats"]).max() < 2e-4
     text = golden["tables"]["text_features"]
     probs, logits, _ = ovit.score(feats, text)

@@ -10,9 +10,9 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libvilgod_b200.so")
-LIB_PATHS = {"bf16": LIB_PATH, "f16": os.path.join(HERE, "lib", "libvilgod_b200_f16.so")}
+LIB_PATHS = {"f16": LIB_PATH, "bf16": os.path.join(HERE, "lib", "libvilgod_b200_bf16.so")}
 
-VG_ABI_VERSION = 1
+VG_ABI_VERSION = 2
 VG_MAX_VIEWS = 16
 VG_VIT_LAYERS = 12
 VG_TILE_ELEMS = 196 * 256
@@ -21,6 +21,7 @@ VG_OK, VG_EINVAL, VG_ESHAPE, VG_EWORKSPACE, VG_EDEGENERATE, VG_ECUDA, VG_ESTATE 
 STATUS_NAMES = {0: "VG_OK", -1: "VG_EINVAL", -2: "VG_ESHAPE", -3: "VG_EWORKSPACE",
                 -4: "VG_EDEGENERATE", -5: "VG_ECUDA", -6: "VG_ESTATE"}
 VG_ROTATE_TORCH_CPU, VG_ROTATE_FUSED, VG_ROTATE_UNFUSED = 0, 1, 2
+VG_DIV_TRUE, VG_DIV_RECIPROCAL = 0, 1
 VG_EPI_BIAS_BF16, VG_EPI_BIAS_QGELU_BF16, VG_EPI_BIAS_RESID_F32 = 0, 1, 2
 
 fp = C.POINTER(C.c_float)
@@ -29,6 +30,7 @@ fp = C.POINTER(C.c_float)
 class VgConfig(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("resolution", C.c_int32), ("depth", C.c_int32),
                 ("image_size", C.c_int32), ("num_views", C.c_int32), ("rotate_mode", C.c_int32),
+                ("div_mode", C.c_int32), ("pool_kernel", C.c_int32), ("pool_pad", C.c_int32),
                 ("obj_ratio", C.c_double), ("depth_bias", C.c_double), ("logit_scale", C.c_double),
                 ("rot", (C.c_float * 9) * VG_MAX_VIEWS), ("gauss", C.c_float * 9)]
 
@@ -88,10 +90,15 @@ SYMBOLS = {
     "vg_vote": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                           C.c_void_p]),
     "vg_classify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
-                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_size_t, C.c_void_p]),
     "vg_test_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "vg_test_gemm_lnf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                   C.c_void_p]),
+    "vg_test_gemm_patch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                     C.c_void_p, C.c_void_p]),
     "vg_test_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "vg_test_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                     C.c_void_p, C.c_void_p]),
@@ -100,8 +107,8 @@ SYMBOLS = {
 _libs = {}
 
 
-def load(operand_dtype="bf16"):
-    """dlopen the bf16- or fp16-operand build and bind every declared symbol (raises if missing)."""
+def load(operand_dtype="f16"):
+    """dlopen the fp16- (default) or bf16-operand build and bind every declared symbol (raises if missing)."""
     if operand_dtype not in LIB_PATHS:
         raise ValueError(f"operand_dtype must be one of {sorted(LIB_PATHS)}")
     if operand_dtype not in _libs:

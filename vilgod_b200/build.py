@@ -10,10 +10,9 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
-LIB_PATH = os.path.join(OUT_DIR, "libvilgod_b200.so")           # bf16 GEMM operands (default)
-LIB_PATH_F16 = os.path.join(OUT_DIR, "libvilgod_b200_f16.so")   # fp16 GEMM operands (-DVG_OPERAND_F16)
-SOURCES = ["api.cu", "canonicalise.cu", "projection.cu", "gemm_tcgen05.cu", "gemm_tcgen05_2cta.cu", "attention.cu",
-           "attention_tcgen05.cu",
+LIB_PATH = os.path.join(OUT_DIR, "libvilgod_b200.so")             # fp16 GEMM operands (default)
+LIB_PATH_BF16 = os.path.join(OUT_DIR, "libvilgod_b200_bf16.so")   # bf16 GEMM operands (-DVG_OPERAND_BF16)
+SOURCES = ["api.cu", "canonicalise.cu", "projection.cu", "gemm_tcgen05.cu", "attention_tcgen05.cu",
            "vit_misc.cu"]
 HEADERS = ["common.cuh", "ptx.cuh", os.path.join("..", "..", "include", "vilgod_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -32,17 +31,17 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False, f16=False):
+def build_library(force=False, verbose=False, bf16=False):
     os.makedirs(OUT_DIR, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
     objs, jobs = [], []
-    lib_path = LIB_PATH_F16 if f16 else LIB_PATH
+    lib_path = LIB_PATH_BF16 if bf16 else LIB_PATH
     for s in SOURCES:
         src = os.path.join(CSRC, s)
-        obj = os.path.join(OUT_DIR, s.replace(".cu", "_f16.o" if f16 else ".o"))
+        obj = os.path.join(OUT_DIR, s.replace(".cu", "_bf16.o" if bf16 else ".o"))
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs):
-            cmd = ([_nvcc()] + NVCC_FLAGS + (["-DVG_OPERAND_F16=1"] if f16 else [])
+            cmd = ([_nvcc()] + NVCC_FLAGS + (["-DVG_OPERAND_BF16=1"] if bf16 else [])
                    + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj])
             jobs.append(cmd)
 
@@ -63,7 +62,7 @@ def build_library(force=False, verbose=False, f16=False):
 
 
 def build_all(force=False, verbose=False):
-    return [build_library(force, verbose, f16=False), build_library(force, verbose, f16=True)]
+    return [build_library(force, verbose, bf16=False), build_library(force, verbose, bf16=True)]
 
 
 if __name__ == "__main__":

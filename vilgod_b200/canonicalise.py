@@ -78,8 +78,16 @@ def canonicalise_packed(points, offsets, transform_to_ego=None):
     else:
         pts = np.array(pts, copy=True)
     n = np.diff(offsets)
-    if np.any(n <= 0):
-        raise ValueError("empty cluster in packed batch")
+    if np.any(n < 0):
+        raise ValueError("offsets must be non-decreasing")
+    if np.any(n == 0):
+        # clusters without points contribute nothing to the packed array: canonicalise the others
+        # (the projection reports VG_EDEGENERATE for the empty ones)
+        keep = np.flatnonzero(n > 0)
+        if keep.size == 0:
+            return np.zeros((0, 3), dtype=np.float32)
+        offsets = np.concatenate([offsets[:-1][keep][:1], offsets[1:][keep]])
+        n = np.diff(offsets)
     seg = np.repeat(np.arange(len(n)), n)
     cx = _segment_median(np.ascontiguousarray(pts[:, 0]), seg, offsets)
     cy = _segment_median(np.ascontiguousarray(pts[:, 1]), seg, offsets)

@@ -18,6 +18,13 @@ constexpr size_t kTileBytesPerImage = (size_t)VG_TILE_ELEMS * 2;
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// A/B switches: set and neither empty nor "0"
+bool env_on(const char *name)
+{
+    const char *v = getenv(name);
+    return v && v[0] && !(v[0] == '0' && v[1] == 0);
+}
+
 struct EncodeBuffers {
     float *x;               // residual stream fp32 [M,768]
     op_t *y;       // attention output (A of out-proj) [M,768]; LayerNorm output when unfused
@@ -128,7 +135,12 @@ int vg_create(const VgConfig *cfg, VgHandle **out)
     *out = nullptr;
     if (cfg->abi_version != VG_ABI_VERSION) return VG_EINVAL;
     if (cfg->num_views < 1 || cfg->num_views > VG_MAX_VIEWS) return VG_ESHAPE;
-    if (cfg->resolution != 112 || cfg->depth != 8 || cfg->image_size != 224) return VG_ESHAPE;
+    if ((cfg->resolution != 112 && cfg->resolution != 224) || cfg->depth != 8 || cfg->image_size != 224)
+        return VG_ESHAPE;
+    // GridToImage is MaxPool3d((1,5,5), stride 1, pad (0,1,1)) in the reference config
+    // (tools/configs/preprocessor/waymo.yaml:81-85); the fused stencil implements exactly that
+    if (cfg->pool_kernel != 5 || cfg->pool_pad != 1) return VG_ESHAPE;
+    if (cfg->div_mode != VG_DIV_TRUE && cfg->div_mode != VG_DIV_RECIPROCAL) return VG_EINVAL;
     VgHandle *h = new (std::nothrow) VgHandle();
     if (!h) return VG_EINVAL;
     h->cfg = *cfg;
@@ -151,14 +163,12 @@ int vg_create(const VgConfig *cfg, VgHandle **out)
             cudaSuccess && qres == cudaDriverEntryPointSuccess)
         h->tma_encode = fn;
     if (projection_init(h) != VG_OK) {
-        delete h;
+        vg_destroy(h);     // frees whatever projection_init had already allocated
         return VG_ECUDA;
     }
-    h->sw.ln_unfused = getenv("VG_LN_UNFUSED") != nullptr;
-    h->sw.gemm_v1 = getenv("VG_GEMM_V1") != nullptr;
-    h->sw.gemm_narrow = getenv("VG_GEMM_NARROW") != nullptr;
-    h->sw.attn_v1 = getenv("VG_ATTN_V1") != nullptr;
-    if (getenv("VG_ATTN_TRACE") && cudaMalloc(&h->attn_trace, 16 * 8 * sizeof(long long)) != cudaSuccess)
+    h->sw.ln_unfused = env_on("VG_LN_UNFUSED");
+    h->sw.gemm_narrow = env_on("VG_GEMM_NARROW");
+    if (env_on("VG_ATTN_TRACE") && cudaMalloc(&h->attn_trace, 16 * 8 * sizeof(long long)) != cudaSuccess)
         h->attn_trace = nullptr;
     *out = h;
     return VG_OK;
@@ -171,6 +181,7 @@ void vg_destroy(VgHandle *h)
     if (h->proj_tables) cudaFree(h->proj_tables);
     if (h->proj_spill) cudaFree(h->proj_spill);
     if (h->proj_spill_flags) cudaFree(h->proj_spill_flags);
+    if (h->proj_img_scratch) cudaFree(h->proj_img_scratch);
     if (h->d_text) cudaFree(h->d_text);
     if (h->d_class_map) cudaFree(h->d_class_map);
     if (h->attn_trace) cudaFree(h->attn_trace);
@@ -281,7 +292,7 @@ int vg_project(VgHandle *h, const float *d_points, const int32_t *d_offsets, int
         VG_SET_ERR(h, "vg_project: null points/offsets or negative cluster count");
         return VG_EINVAL;
     }
-    return launch_projection(h, d_points, d_offsets, C, static_cast<op_t *>(d_tiles), d_u8,
+    return launch_projection(h, d_points, d_offsets, C, static_cast<op_t *>(d_tiles), d_u8, false,
                              d_status, dbg, static_cast<cudaStream_t>(stream));
 }
 
@@ -331,7 +342,8 @@ int vg_vote(VgHandle *h, const float *d_probs, const int32_t *d_top1, int32_t C,
 
 int vg_classify(VgHandle *h, const float *d_points, const int32_t *d_offsets, int32_t C,
                 float *d_probs, int32_t *d_top1, float *d_feats, int32_t *d_voted_class,
-                float *d_voted_score, int32_t *d_status, void *d_ws, size_t ws_bytes, void *stream)
+                float *d_voted_score, int32_t *d_status, uint8_t *d_u8_first, void *d_ws,
+                size_t ws_bytes, void *stream)
 {
     if (!h) return VG_EINVAL;
     if (C < 0 || (C > 0 && (!d_points || !d_offsets || !d_probs || !d_top1 || !d_ws)))
@@ -362,7 +374,8 @@ int vg_classify(VgHandle *h, const float *d_points, const int32_t *d_offsets, in
     const int P = h->num_prompts;
     for (int64_t c0 = 0; c0 < C; c0 += cc) {
         const int64_t n = C - c0 < cc ? C - c0 : cc;
-        int rc = launch_projection(h, d_points, d_offsets + c0, (int32_t)n, tiles, nullptr,
+        int rc = launch_projection(h, d_points, d_offsets + c0, (int32_t)n, tiles,
+                                   d_u8_first ? d_u8_first + (size_t)c0 * 224 * 224 : nullptr, true,
                                    d_status ? d_status + c0 : nullptr, nullptr, st);
         if (rc) return rc;
         rc = encode_chunk(h, tiles, n * V, eb, d_probs + c0 * V * P, d_top1 + c0 * V,
@@ -381,6 +394,29 @@ int vg_test_gemm(VgHandle *h, const void *d_a, const void *d_w, const float *d_b
     if (epilogue < 0 || epilogue > VG_EPI_BIAS_RESID_F32) return VG_EINVAL;
     GemmArgs g{static_cast<const op_t *>(d_a), static_cast<const op_t *>(d_w),
                d_bias, d_out, M, N, K, epilogue};
+    return launch_gemm(h, g, static_cast<cudaStream_t>(stream));
+}
+
+int vg_test_gemm_lnf(VgHandle *h, const void *d_a, const void *d_w, const float *d_bias,
+                     const float *d_colsum, float *d_stats, void *d_xb_out, int64_t M, int32_t N,
+                     int32_t K, int32_t epilogue, void *d_out, void *stream)
+{
+    if (!h || !d_a || !d_w || !d_bias || !d_out || !d_stats) return VG_EINVAL;
+    if (epilogue < 0 || epilogue > VG_EPI_BIAS_RESID_F32) return VG_EINVAL;
+    GemmArgs g{static_cast<const op_t *>(d_a), static_cast<const op_t *>(d_w),
+               d_bias, d_out, M, N, K, epilogue};
+    g.stats = d_stats;
+    g.colsum = d_colsum;
+    g.xb_out = static_cast<op_t *>(d_xb_out);
+    return launch_gemm(h, g, static_cast<cudaStream_t>(stream));
+}
+
+int vg_test_gemm_patch(VgHandle *h, const void *d_tiles, const void *d_w, const float *d_table,
+                       int64_t B, float *d_x, void *stream)
+{
+    if (!h || !d_tiles || !d_w || !d_table || !d_x || B < 0) return VG_EINVAL;
+    GemmArgs g{static_cast<const op_t *>(d_tiles), static_cast<const op_t *>(d_w), d_table, d_x,
+               B * kPatches, kWidth, kPatchK, kEpiPatch};
     return launch_gemm(h, g, static_cast<cudaStream_t>(stream));
 }
 

@@ -404,32 +404,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, op_t *__restric
 
 }  // namespace
 
-int launch_attention_tc(VgHandle *h, const op_t *qkv, int64_t B, op_t *out,
-                        cudaStream_t st)
+int launch_attention(VgHandle *h, const op_t *qkv, int64_t B, op_t *out, cudaStream_t st)
 {
     if (B <= 0) return VG_OK;
-    auto encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(h->tma_encode);
-    if (!encode) {
-        VG_SET_ERR(h, "cuTensorMapEncodeTiled entry point unavailable");
-        return VG_ECUDA;
-    }
     CUtensorMap map;
-    const cuuint64_t gdim[3] = {3 * kWidth, (cuuint64_t)L, (cuuint64_t)B};
-    const cuuint64_t gstride[2] = {3 * kWidth * 2, (cuuint64_t)L * 3 * kWidth * 2};
-    const cuuint32_t box[3] = {HD, LP, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<op_t *>(qkv),
-                        gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        VG_SET_ERR(h, "attention: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
-        return VG_ECUDA;
-    }
-    // per device and cheap: set on every launch rather than caching in process-wide state
-    VG_CUDA_CHECK(h, cudaFuncSetAttribute(attention_tc_kernel,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)SMEM_BYTES));
+    int rc = make_tmap_nd(h, &map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, 3, 3 * kWidth, (uint64_t)L,
+                          (uint64_t)B, HD, LP);
+    if (rc) return rc;
+    if ((rc = vg_set_smem_once(h, reinterpret_cast<const void *>(attention_tc_kernel), SMEM_BYTES))) return rc;
     const int64_t items = B * kHeads;
     const int grid = (int)(items < h->num_sms ? items : h->num_sms);
     VgProfScope prof(h, VG_K_ATTENTION, 4.0 * (double)B * kHeads * L * L * HD, st);

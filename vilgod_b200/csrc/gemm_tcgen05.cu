@@ -1,21 +1,24 @@
-// Persistent, warp-specialised bf16 GEMM on the 5th-generation tensor cores (tcgen05 + TMEM),
-// operands staged by TMA -- the linear layers of the CLIP ViT-B/16 visual tower:
-//   patch embedding (folded conv1)      third_party/CLIP/clip/model.py:224-229
-//   attention in-proj / out-proj        third_party/CLIP/clip/model.py:187 (nn.MultiheadAttention)
-//   MLP c_fc (+QuickGELU) / c_proj      third_party/CLIP/clip/model.py:177-181,191
+// 2-CTA (cta_group::2) persistent bf16 GEMM with TMA-store epilogues -- the production path for
+// the QKV / out-proj / MLP layers of the CLIP visual tower (third_party/CLIP/clip/model.py:177-192).
 //
-//   D[M,N] = epilogue( A[M,K] . W[N,K]^T + bias[N] ),  A / W bf16 row-major (both K-major), fp32
-//   accumulation in tensor memory.
+//   D[M,N] = epilogue( A[M,K] . W[N,K]^T + bias[N] )
 //
-// CTA = 6 warps on one SM (one CTA per SM, grid = min(#tiles, #SMs), static round-robin tiles):
-//   warp 0      TMA producer : 4-stage ring of {A 128x64, W 256x64} bf16 tiles, SWIZZLE_128B
-//   warp 1      MMA issuer   : tcgen05.mma.cta_group::1.kind::f16, UMMA 128x256x16, one elected lane;
-//                              owns the 512-column TMEM allocation (2 accumulator stages x 256)
-//   warps 2..5  epilogue     : tcgen05.ld 32x32b -> registers -> bias / QuickGELU / residual ->
-//                              global; overlaps the next tile's main loop through the second
-//                              accumulator stage
-// Synchronisation is mbarrier-only: full/empty per smem stage (TMA tx-count / tcgen05.commit) and
-// full/empty per accumulator stage (tcgen05.commit / 128 epilogue arrivals).
+// Why a CTA pair: a single-CTA 128x256 SS-mode MMA streams 12 KB of operands per K=16 step out of
+// shared memory while TMA writes the same amount in -- 192 B/clk against a 128 B/clk shared-memory
+// port, which capped the first kernel at ~67 % tensor-pipe activity (profiles/r01_ncu_v1_*).  With
+// cta_group::2 the pair computes a 256x256 tile, each CTA stages its own 128 A rows and only HALF
+// of the W tile (128 rows); the tensor cores read the other half from the peer's shared memory.
+//
+// Per CTA (6 warps), clusters of 2 CTAs, one cluster per SM pair, static round-robin over tiles:
+//   warp 0     TMA producer (both CTAs): A 128x64 + W 128x64 per stage, bytes credited to the
+//              LEADER's full barrier (cp.async.bulk.tensor ... cta_group::2)
+//   warp 1     leader only: tcgen05.mma.cta_group::2 (UMMA 256x256x16), multicast tcgen05.commit
+//              frees the stage in both CTAs / publishes the accumulator to both epilogues
+//   warps 2-5  epilogue (both CTAs, 32 TMEM lanes each): tcgen05.ld -> registers -> bias /
+//              QuickGELU / residual -> swizzled staging slab in shared memory -> TMA store
+//              (coalesced, asynchronous, clips the ragged last M tile).  The fp32 residual stream is
+//              TMA-loaded into the slab one chunk ahead, so the epilogue issues no per-thread global
+//              loads or stores at all.
 #include <cudaTypedefs.h>
 #include <stdlib.h>
 
@@ -25,260 +28,517 @@
 namespace vg {
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64, UK = 16;
-constexpr int STAGES = 4;
+constexpr int BM = 128;            // rows per CTA (256 per pair)
+constexpr int BN = 256;            // UMMA N; each CTA stages BN/2 rows of W
+constexpr int BK = 64, UK = 16;
 constexpr int ACC_STAGES = 2;
-constexpr int A_BYTES = BM * BK * 2;   // 16 KiB
-constexpr int B_BYTES = BN * BK * 2;   // 32 KiB
+constexpr int A_BYTES = BM * BK * 2;          // 16 KiB
+constexpr int B_BYTES = (BN / 2) * BK * 2;    // 16 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int GEMM_THREADS = 192;
-constexpr int EPI_THREADS = 128;
-constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int SLAB_BYTES = 4096;              // 32 rows x 128 B, SWIZZLE_128B
+// bf16 epilogues (bias, QuickGELU) are instruction-bound: 8 warps, two per TMEM lane quarter, each
+// owning half of the 256 columns.  The fp32 residual epilogue is memory-bound: 4 warps.
+// LNF ("LayerNorm folded"):
+//   residual epilogue  : additionally emits a bf16 copy of the new residual stream (the next
+//                        GEMM's A operand) and accumulates per-row sum / sum-of-squares
+//   bf16 epilogues     : A is the RAW residual stream in bf16, W carries the LayerNorm gain, and the
+//                        normalisation is applied after the matmul:
+//                        y = rstd_i * (acc - mu_i * colsum_n) + c_n      (model.py:157-163,190-191)
+// RMODE (residual epilogue only) trades epilogue resources against operand stages:
+//   kNarrow  4 warps, double-buffered out slabs, 4 operand stages          (non-LN-folded path, tests)
+//   kWide    8 warps (two per TMEM lane quarter, half of the columns each), single out slabs, 3 stages:
+//            the K = 768 out-proj GEMM moves 9 KB of residual traffic per row for 0.23 GFLOP per
+//            image-layer, so its epilogue (not the tensor pipe) sets the pace
+//   kDeep    4 warps, single out slabs, 5 stages: the K = 3072 c_proj GEMM is tensor bound and streams
+//            11 GB per launch next to its operands, so it wants the deeper TMA ring instead
+enum : int { kNarrow = 0, kWide = 1, kDeep = 2 };
+template <int EPI, bool LNF, int RMODE = kNarrow> struct EpiCfg {
+    static constexpr bool kResid = EPI == VG_EPI_BIAS_RESID_F32;
+    static constexpr bool kSlim = RMODE != kNarrow;          // 2 in + 1 out + 1 bf16 out per warp
+    static constexpr int kWarps = kResid ? (RMODE == kWide ? 8 : 4) : 8;
+    static constexpr int kSlabs = kResid ? (kSlim ? 4 : 2 + 2 + (LNF ? 2 : 0)) : 2;
+    static constexpr int kThreads = 64 + 32 * kWarps;
+    static constexpr int kStages = kResid ? (RMODE == kWide ? 3 : RMODE == kDeep ? 5 : 4) : 5;
+    static constexpr int kEpiBytes = kWarps * kSlabs * SLAB_BYTES;          // 64 / 96 / 128 KiB
+    static constexpr int kXchgBytes = RMODE == kWide ? 4 * 32 * 2 * 4 : 0;   // row-statistics hand-off
+    static constexpr size_t kSmem = (size_t)kStages * STAGE_BYTES + kEpiBytes + 1024 + 512 + kXchgBytes;
+};
 
-struct GemmParams {
-    const float *bias;
-    void *out;
+struct Params {
+    const float *bias;       // [N]: bias, or c_n for LN-folded epilogues
+    const float *colsum;     // [N]: sum_k W'[n][k] (LN-folded bf16 epilogues)
+    float *stats;            // [M][3][2] per 256-column tile: row sum / sum of squares of the residual
     int64_t M;
     int32_t N, K;
 };
 
 __device__ __forceinline__ float quick_gelu(float v)
 {
-    // x * sigmoid(1.702 x)   (model.py:166-168)
-    return __fdividef(v, 1.0f + __expf(-1.702f * v));
+    // x * sigmoid(1.702 x) with sigmoid(z) = 0.5 * tanh(z / 2) + 0.5: one MUFU op per element
+    // (tanh.approx, relative error ~2^-11, below the bf16 rounding of the output)
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * v));
+    return v * fmaf(0.5f, t, 0.5f);
 }
+// 16-byte chunk c of row r inside a 1024-byte-aligned SWIZZLE_128B slab
+__device__ __forceinline__ uint32_t slab_off(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
 
-
-template <int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-            const GemmParams p)
+template <int EPI, bool LNF, int RMODE, bool PATCH>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<EPI, LNF, RMODE>::kThreads, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+             const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_xb,
+             const Params p)
 {
+    using Cfg = EpiCfg<EPI, LNF, RMODE>;
+    constexpr bool WIDE = RMODE == kWide, SLIM = RMODE != kNarrow;
+    constexpr int XIN = 2;       // fp32 residual slabs in flight per epilogue warp
+    constexpr int STAGES = Cfg::kStages;
+    constexpr int EPI_BYTES = Cfg::kEpiBytes;
     extern __shared__ unsigned char smem_raw[];
-    // SWIZZLE_128B tiles need 1024-byte alignment
     unsigned char *smem = reinterpret_cast<unsigned char *>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * STAGE_BYTES);
-    uint64_t *full_bar = bars;                               // [STAGES]
-    uint64_t *empty_bar = bars + STAGES;                     // [STAGES]
-    uint64_t *tmem_full = bars + 2 * STAGES;                 // [ACC_STAGES]
-    uint64_t *tmem_empty = bars + 2 * STAGES + ACC_STAGES;   // [ACC_STAGES]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 2 * ACC_STAGES);
+    unsigned char *epi_smem = smem + (size_t)STAGES * STAGE_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(epi_smem + EPI_BYTES);
+    uint64_t *full_bar = bars;                               // [STAGES]   (leader's are used)
+    uint64_t *empty_bar = bars + STAGES;                     // [STAGES]   (per CTA)
+    uint64_t *tmem_full = bars + 2 * STAGES;                 // [ACC]      (per CTA)
+    uint64_t *tmem_empty = bars + 2 * STAGES + ACC_STAGES;   // [ACC]      (leader's are used)
+    constexpr int EPI_WARPS = Cfg::kWarps;
+    constexpr int SLABS_PER_WARP = Cfg::kSlabs;
+    uint64_t *xin_bar = bars + 2 * STAGES + 2 * ACC_STAGES;  // [epilogue warps][XIN] (fp32 residual path)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(xin_bar + 16);
+    float *xstat = reinterpret_cast<float *>(epi_smem + EPI_BYTES + 512);   // [4 quarters][32][2] (WIDE)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tiles = (int)((p.M + BM - 1) / BM);
+    const uint32_t rank = ptx::cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    // PATCH: one pair tile = the 196 patch rows of one image (rows 196..255 are zero-filled by TMA and
+    // clipped on the way out), so that token = 1 + row never straddles two images
+    const int m_tiles = PATCH ? (int)(p.M / kPatches) : (int)((p.M + 2 * BM - 1) / (2 * BM));
     const int n_tiles = p.N / BN;
     const int num_tiles = m_tiles * n_tiles;
     const int num_kb = p.K / BK;
+    // fp32 rows added in the residual epilogue: the residual stream itself, or (PATCH) the
+    // [197,768] table b_eff + positional embedding, whose map travels in the tma_xb slot
+    const CUtensorMap *xin_map = PATCH ? &tma_xb : &tma_out;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tma_a);
         ptx::prefetch_tensormap(&tma_b);
+        ptx::prefetch_tensormap(&tma_out);
+        if (EPI == VG_EPI_BIAS_RESID_F32 && (LNF || PATCH)) ptx::prefetch_tensormap(&tma_xb);
         for (int s = 0; s < STAGES; ++s) {
             ptx::mbar_init(&full_bar[s], 1);
             ptx::mbar_init(&empty_bar[s], 1);
         }
         for (int s = 0; s < ACC_STAGES; ++s) {
             ptx::mbar_init(&tmem_full[s], 1);
-            ptx::mbar_init(&tmem_empty[s], EPI_THREADS);
+            ptx::mbar_init(&tmem_empty[s], 2 * EPI_WARPS);   // one arrival per epilogue warp, both CTAs
         }
+        for (int s = 0; s < 16; ++s) ptx::mbar_init(&xin_bar[s], 1);
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(tmem_slot, ACC_STAGES * BN);
-        ptx::tmem_relinquish();
+        ptx::tmem_alloc_pair(tmem_slot, ACC_STAGES * BN);
+        ptx::tmem_relinquish_pair();
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    __syncwarp();
+    ptx::cluster_sync_all();     // peer barriers initialised, both TMEM allocations done
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ================= TMA producer =================
+        // ================= TMA producer (both CTAs) =================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+                const int a_row = m_blk * 2 * BM + (int)rank * BM;
+                const int b_row = n_blk * BN + (int)rank * (BN / 2);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
                     unsigned char *sa = smem + (size_t)stage * STAGE_BYTES;
-                    unsigned char *sb = sa + A_BYTES;
-                    ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-                    ptx::tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
-                    ptx::tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+                    if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+                    if (PATCH) ptx::tma_load_3d_pair(sa, &tma_a, &full_bar[stage], kb * BK, (int)rank * BM, m_blk);
+                    else ptx::tma_load_2d_pair(sa, &tma_a, &full_bar[stage], kb * BK, a_row);
+                    ptx::tma_load_2d_pair(sa + A_BYTES, &tma_b, &full_bar[stage], kb * BK, b_row);
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(BM, BN, kOpFormat);
+        // ================= MMA issuer (leader CTA, one lane) =================
+        // The leader's whole warp runs the loop convergently; one elected lane issues the tcgen05
+        // instructions.  With a lone divergent lane ptxas wraps every UTCHMMA in an ELECT / R2UR
+        // waterfall; convergent code keeps descriptors and TMEM addresses in uniform registers.
+        if (leader) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(2 * BM, BN, kOpFormat);
+            const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
             int stage = 0, as = 0;
             uint32_t phase = 0, aphase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 ptx::mbar_wait(&tmem_empty[as], aphase ^ 1u);
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+                const uint32_t d_tmem = tb + (uint32_t)(as * BN);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
                     const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * STAGE_BYTES);
                     const uint64_t da = ptx::make_kmajor_sw128_desc(sa);
                     const uint64_t db = ptx::make_kmajor_sw128_desc(sa + A_BYTES);
+                    if (ptx::elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / UK; ++k) {
-                        // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle atom:
-                        // +2 in the 16-byte units of the descriptor's start-address field
-                        ptx::mma_f16_ss(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                                        (uint32_t)((kb | k) != 0));
+                        for (int k = 0; k < BK / UK; ++k)
+                            ptx::mma_f16_ss_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k),
+                                                 idesc, (uint32_t)((kb | k) != 0));
+                        ptx::tc_commit_pair(&empty_bar[stage], 3);   // stage free in both CTAs
                     }
-                    ptx::tc_commit(&empty_bar[stage]);   // frees the smem stage when the MMAs retire
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
-                ptx::tc_commit(&tmem_full[as]);          // accumulator ready for the epilogue
+                if (ptx::elect_one()) ptx::tc_commit_pair(&tmem_full[as], 3);   // accumulator ready
+                __syncwarp();
                 if (++as == ACC_STAGES) { as = 0; aphase ^= 1u; }
             }
         }
     } else {
-        // ================= epilogue warps =================
-        const int lane_base = (warp & 3) * 32;   // TMEM lanes this warp may touch
+        // ================= epilogue warps (both CTAs) =================
+        const int ew = warp & 3;                  // TMEM lane quarter this warp may touch
+        const int chalf = (warp - 2) >> 2;        // column half (8-warp epilogues), else 0
+        const int lane_base = ew * 32;
+        unsigned char *slab = epi_smem + (size_t)(warp - 2) * SLABS_PER_WARP * SLAB_BYTES;
+        uint64_t *xbar = xin_bar + XIN * (warp - 2);
+        uint32_t xphase = 0u;                     // one phase bit per residual slab
         int as = 0;
         uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int obuf = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
             const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
-            ptx::mbar_wait(&tmem_full[as], aphase);
-            ptx::tc_fence_after();
-            const int64_t row = (int64_t)m_blk * BM + lane_base + lane;
-            const bool row_ok = row < p.M;
-            int64_t orow = row;
-            const float *brow = p.bias;
-            if (EPI == kEpiPatch) {
-                // A row = img*196 + patch  ->  residual-stream row img*197 + 1 + patch;
-                // "bias" is the [197,768] table b_eff + positional embedding
-                const int64_t img = row / kPatches;
-                const int patch = (int)(row - img * kPatches);
-                orow = img * kTokens + 1 + patch;
-                brow = p.bias + (size_t)(1 + patch) * p.N;
+            // first row of the slab; PATCH: token index inside image m_blk
+            const int row0 = PATCH ? 1 + (int)rank * BM + lane_base : m_blk * 2 * BM + (int)rank * BM + lane_base;
+            if (PATCH && (int)rank * BM + lane_base >= kPatches) {   // no patch row in this warp's lanes
+                ptx::mbar_wait(&tmem_full[as], aphase);
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive_remote(&tmem_empty[as], 0);
+                if (++as == ACC_STAGES) { as = 0; aphase ^= 1u; }
+                continue;
             }
-#pragma unroll 1
-            for (int chunk = 0; chunk < BN / 32; ++chunk) {
-                uint32_t r[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) +
-                                       (uint32_t)(as * BN + chunk * 32);
-                ptx::tmem_ld_32x32b_x32(taddr, r);
-                ptx::tmem_ld_wait();
-                const int n0 = n_blk * BN + chunk * 32;
-                if (row_ok) {
-                    const float4 *b4 = reinterpret_cast<const float4 *>(brow + n0);
-                    if (EPI == VG_EPI_BIAS_BF16 || EPI == VG_EPI_BIAS_QGELU_BF16) {
-                        uint4 *dst = reinterpret_cast<uint4 *>(
-                            reinterpret_cast<op_t *>(p.out) + orow * p.N + n0);
+            const int col0 = n_blk * BN;
+            const uint32_t tbase = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(as * BN);
+
+            if (EPI == VG_EPI_BIAS_RESID_F32) {
+                // fp32 residual stream in chunks of 32 columns; the x chunk one ahead is in flight while
+                // chunk j is combined.  Narrow: one warp per lane quarter takes all 8 chunks, slabs
+                // [0,2) = x in, 2,3 = x out, 4,5 = bf16 out.  Slim (wide / deep): slabs [0,2) = x in,
+                // 2 = x out, 3 = bf16 out; wide: two warps per quarter take 4 chunks each.
+                constexpr int NCH = WIDE ? 4 : BN / 32;
+                constexpr int OUT0 = XIN, XB0 = SLIM ? XIN + 1 : XIN + 2;
+                const int ch0 = WIDE ? chalf * NCH : 0;
+                if (lane == 0) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float v[8];
-                            const float4 ba = __ldg(b4 + 2 * q), bb = __ldg(b4 + 2 * q + 1);
-                            const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                v[j] = __uint_as_float(r[8 * q + j]) + bv[j];
-                                if (EPI == VG_EPI_BIAS_QGELU_BF16) v[j] = quick_gelu(v[j]);
-                            }
-                            dst[q] = make_uint4(pack_op(v[0], v[1]), pack_op(v[2], v[3]),
-                                                pack_op(v[4], v[5]), pack_op(v[6], v[7]));
-                        }
-                    } else {
-                        float4 *dst =
-                            reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + orow * p.N + n0);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 bv = __ldg(b4 + q);
-                            float4 o;
-                            o.x = __uint_as_float(r[4 * q + 0]) + bv.x;
-                            o.y = __uint_as_float(r[4 * q + 1]) + bv.y;
-                            o.z = __uint_as_float(r[4 * q + 2]) + bv.z;
-                            o.w = __uint_as_float(r[4 * q + 3]) + bv.w;
-                            if (EPI == VG_EPI_BIAS_RESID_F32) {   // x += attn / mlp branch
-                                const float4 x = dst[q];
-                                o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
-                            }
-                            dst[q] = o;
-                        }
+                    for (int j = 0; j < XIN - 1 + (SLIM ? 1 : 0); ++j) {
+                        ptx::mbar_arrive_expect_tx(&xbar[j], SLAB_BYTES);
+                        ptx::tma_load_2d(slab + j * SLAB_BYTES, xin_map, &xbar[j], col0 + (ch0 + j) * 32, row0);
                     }
                 }
+                ptx::mbar_wait(&tmem_full[as], aphase);
+                ptx::tc_fence_after();
+                float rs = 0.0f, rq = 0.0f;      // row sum / sum of squares of the new residual (LNF)
+#pragma unroll 1
+                for (int c = 0; c < NCH; ++c) {
+                    const int ch = ch0 + c;
+                    const int ib = c % XIN;
+                    if (!SLIM && lane == 0 && c + XIN - 1 < NCH) {
+                        // that slab was fully read in iteration c-1 (fence + __syncwarp below)
+                        const int nb = (c + XIN - 1) % XIN;
+                        ptx::mbar_arrive_expect_tx(&xbar[nb], SLAB_BYTES);
+                        ptx::tma_load_2d(slab + nb * SLAB_BYTES, xin_map, &xbar[nb],
+                                         col0 + (ch + XIN - 1) * 32, row0);
+                    }
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32b_x32(tbase + (uint32_t)(ch * 32), r);
+                    // the out slab about to be overwritten must have been drained by its TMA store
+                    if (lane == 0) {
+                        if (SLIM) ptx::tma_store_wait_read<0>();
+                        else ptx::tma_store_wait_read<1>();
+                    }
+                    __syncwarp();
+                    ptx::mbar_wait(&xbar[ib], (xphase >> ib) & 1u);
+                    xphase ^= 1u << ib;
+                    ptx::tmem_ld_wait();
+                    const unsigned char *xin = slab + ib * SLAB_BYTES;
+                    unsigned char *xout = slab + (OUT0 + (SLIM ? 0 : obuf)) * SLAB_BYTES;
+                    unsigned char *xb = slab + (XB0 + (SLIM ? 0 : ((c >> 1) & 1))) * SLAB_BYTES;
+                    const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + col0 + ch * 32);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint32_t off = slab_off(lane, q);
+                        const float4 x = *reinterpret_cast<const float4 *>(xin + off);
+                        const float4 bv = PATCH ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(b4 + q);
+                        float4 o;
+                        o.x = x.x + (__uint_as_float(r[4 * q + 0]) + bv.x);
+                        o.y = x.y + (__uint_as_float(r[4 * q + 1]) + bv.y);
+                        o.z = x.z + (__uint_as_float(r[4 * q + 2]) + bv.z);
+                        o.w = x.w + (__uint_as_float(r[4 * q + 3]) + bv.w);
+                        *reinterpret_cast<float4 *>(xout + off) = o;
+                        if (LNF) {
+                            rs += (o.x + o.y) + (o.z + o.w);
+                            rq += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+                            // bf16 copy: two 32-column chunks share one 64-column slab row (128 B)
+                            uint2 pk = make_uint2(pack_op(o.x, o.y), pack_op(o.z, o.w));
+                            *reinterpret_cast<uint2 *>(xb + slab_off(lane, (c & 1) * 4 + (q >> 1)) +
+                                                       (q & 1) * 8) = pk;
+                        }
+                    }
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (SLIM && c + XIN < NCH) {      // refill the x slab this chunk has just consumed
+                            ptx::mbar_arrive_expect_tx(&xbar[ib], SLAB_BYTES);
+                            ptx::tma_load_2d(slab + ib * SLAB_BYTES, xin_map, &xbar[ib],
+                                             col0 + (ch + XIN) * 32, row0);
+                        }
+                        if (PATCH) ptx::tma_store_3d(&tma_out, xout, col0 + ch * 32, row0, m_blk);
+                        else ptx::tma_store_2d(&tma_out, xout, col0 + ch * 32, row0);
+                        if (LNF && (c & 1))   // same bulk group as this chunk's fp32 store
+                            ptx::tma_store_2d(&tma_xb, xb, col0 + (ch - 1) * 32, row0);
+                        ptx::tma_store_commit();
+                    }
+                    obuf ^= 1;
+                }
+                if (LNF) {
+                    if (WIDE) {     // the column-half partner's partial sums, added in fixed order
+                        float2 *xs = reinterpret_cast<float2 *>(xstat) + lane_base + lane;
+                        if (chalf == 1) *xs = make_float2(rs, rq);
+                        asm volatile("bar.sync %0, 64;" ::"r"(1 + ew) : "memory");
+                        if (chalf == 0) {
+                            const float2 o = *xs;
+                            rs += o.x;
+                            rq += o.y;
+                        }
+                        asm volatile("bar.sync %0, 64;" ::"r"(1 + ew) : "memory");
+                    }
+                    const int64_t row = (int64_t)row0 + lane;
+                    // one slot per 256-column tile, summed in fixed order by the consumer:
+                    // deterministic (no atomics) and nothing to clear between GEMMs
+                    if (row < p.M && (!WIDE || chalf == 0))
+                        *reinterpret_cast<float2 *>(p.stats + 6 * row + 2 * n_blk) = make_float2(rs, rq);
+                }
+            } else {
+                // bf16 output: this warp's half of the tile in 2 chunks of 64 columns,
+                // slabs 0,1 = out (2 x [32 rows x 64 bf16])
+                float mu = 0.0f, rstd = 1.0f;
+                if (LNF) {
+                    const int64_t row = (int64_t)row0 + lane;
+                    if (row < p.M) {
+                        const float2 *sp = reinterpret_cast<const float2 *>(p.stats + 6 * row);
+                        const float2 s0 = sp[0], s1 = sp[1], s2 = sp[2];
+                        mu = ((s0.x + s1.x) + s2.x) * (1.0f / kWidth);
+                        const float var = fmaxf(((s0.y + s1.y) + s2.y) * (1.0f / kWidth) - mu * mu, 0.0f);
+                        rstd = rsqrtf(var + 1e-5f);
+                    }
+                }
+                const float nmu = -mu;
+                ptx::mbar_wait(&tmem_full[as], aphase);
+                ptx::tc_fence_after();
+#pragma unroll 1
+                for (int ch = 2 * chalf; ch < 2 * chalf + 2; ++ch) {
+                    uint32_t r0[32], r1[32];
+                    ptx::tmem_ld_32x32b_x32(tbase + (uint32_t)(ch * 64), r0);
+                    ptx::tmem_ld_32x32b_x32(tbase + (uint32_t)(ch * 64 + 32), r1);
+                    if (lane == 0) ptx::tma_store_wait_read<1>();
+                    __syncwarp();
+                    ptx::tmem_ld_wait();
+                    unsigned char *out = slab + obuf * SLAB_BYTES;
+                    const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + col0 + ch * 64);
+                    const float4 *s4 = reinterpret_cast<const float4 *>(p.colsum + col0 + ch * 64);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint32_t *src = q < 4 ? &r0[8 * q] : &r1[8 * (q - 4)];
+                        const float4 ba = __ldg(b4 + 2 * q), bb = __ldg(b4 + 2 * q + 1);
+                        float v[8];
+                        if (LNF) {
+                            const float4 sa = __ldg(s4 + 2 * q), sb = __ldg(s4 + 2 * q + 1);
+                            const float sv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+                            const float cv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                v[j] = fmaf(rstd, fmaf(nmu, sv[j], __uint_as_float(src[j])), cv[j]);
+                        } else {
+                            v[0] = __uint_as_float(src[0]) + ba.x; v[1] = __uint_as_float(src[1]) + ba.y;
+                            v[2] = __uint_as_float(src[2]) + ba.z; v[3] = __uint_as_float(src[3]) + ba.w;
+                            v[4] = __uint_as_float(src[4]) + bb.x; v[5] = __uint_as_float(src[5]) + bb.y;
+                            v[6] = __uint_as_float(src[6]) + bb.z; v[7] = __uint_as_float(src[7]) + bb.w;
+                        }
+                        if (EPI == VG_EPI_BIAS_QGELU_BF16) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = quick_gelu(v[j]);
+                        }
+                        *reinterpret_cast<uint4 *>(out + slab_off(lane, q)) =
+                            make_uint4(pack_op(v[0], v[1]), pack_op(v[2], v[3]),
+                                       pack_op(v[4], v[5]), pack_op(v[6], v[7]));
+                    }
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::tma_store_2d(&tma_out, out, col0 + ch * 64, row0);
+                        ptx::tma_store_commit();
+                    }
+                    obuf ^= 1;
+                }
             }
+            // accumulator stage drained: tell the leader's MMA warp (one arrival per warp)
             ptx::tc_fence_before();
-            ptx::mbar_arrive(&tmem_empty[as]);
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_remote(&tmem_empty[as], 0);
             if (++as == ACC_STAGES) { as = 0; aphase ^= 1u; }
         }
+        if (lane == 0) ptx::tma_store_wait_all<0>();
     }
 
     ptx::tc_fence_before();
-    __syncthreads();
+    __syncwarp();
+    ptx::cluster_sync_all();     // nobody may still touch the peer's smem / TMEM / barriers
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, ACC_STAGES * BN);
+        ptx::tmem_dealloc_pair(tmem_base, ACC_STAGES * BN);
     }
 }
 
-int make_tmap_2d(VgHandle *h, CUtensorMap *map, const void *ptr, uint64_t rows, uint64_t cols,
-                 uint32_t box_rows, uint32_t box_cols)
+}  // namespace
+
+// Tensor maps are cached per handle, keyed by (pointer, shape, box, type): the weights and the
+// caller's workspace keep their addresses from one launch to the next, so after the first chunk a
+// launch costs a table lookup instead of three or four cuTensorMapEncodeTiled calls.
+int make_tmap_nd(VgHandle *h, CUtensorMap *map, CUtensorMapDataType dt, int elt_bytes, const void *ptr,
+                 int rank, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1)
 {
+    const uint64_t key[6] = {reinterpret_cast<uint64_t>(ptr), d0, d1, d2,
+                             ((uint64_t)box0 << 32) | box1, ((uint64_t)dt << 8) | (uint64_t)rank};
+    for (const VgTmapEntry &e : h->tmaps)
+        if (memcmp(e.key, key, sizeof(key)) == 0) {
+            *map = e.map;
+            return VG_OK;
+        }
     auto encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(h->tma_encode);
     if (!encode) {
         VG_SET_ERR(h, "cuTensorMapEncodeTiled entry point unavailable");
         return VG_ECUDA;
     }
-    const cuuint64_t gdim[2] = {cols, rows};
-    const cuuint64_t gstride[1] = {cols * sizeof(op_t)};
-    const cuuint32_t box[2] = {box_cols, box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), gdim,
-                        gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const cuuint64_t gdim[3] = {d0, d1, d2};
+    const cuuint64_t gstride[2] = {d0 * (uint64_t)elt_bytes, d0 * d1 * (uint64_t)elt_bytes};
+    const cuuint32_t box[3] = {box0, box1, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(map, dt, (cuuint32_t)rank, const_cast<void *>(ptr), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        VG_SET_ERR(h, "cuTensorMapEncodeTiled failed (CUresult %d) rows=%llu cols=%llu", (int)r,
-                   (unsigned long long)rows, (unsigned long long)cols);
+        VG_SET_ERR(h, "cuTensorMapEncodeTiled failed (CUresult %d) rank=%d dims=%llu,%llu,%llu", (int)r,
+                   rank, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2);
         return VG_ECUDA;
     }
+    if (h->tmaps.size() >= 1024) h->tmaps.clear();      // callers that keep moving their buffers
+    VgTmapEntry e;
+    memcpy(e.key, key, sizeof(key));
+    e.map = *map;
+    h->tmaps.push_back(e);
     return VG_OK;
 }
 
-template <int EPI>
-int launch_gemm_t(VgHandle *h, const GemmArgs &g, cudaStream_t st)
+namespace {
+
+int make_tmap(VgHandle *h, CUtensorMap *map, CUtensorMapDataType dt, int elt_bytes, const void *ptr,
+              uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols)
 {
-    CUtensorMap ta, tb;
-    int rc = make_tmap_2d(h, &ta, g.a, (uint64_t)g.M, (uint64_t)g.K, BM, BK);
+    return make_tmap_nd(h, map, dt, elt_bytes, ptr, 2, cols, rows, 1, box_cols, box_rows);
+}
+
+int make_tmap3(VgHandle *h, CUtensorMap *map, CUtensorMapDataType dt, int elt_bytes, const void *ptr,
+               uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1)
+{
+    return make_tmap_nd(h, map, dt, elt_bytes, ptr, 3, d0, d1, d2, box0, box1);
+}
+
+template <int EPI, bool LNF, int RMODE = kNarrow>
+int launch_t(VgHandle *h, const GemmArgs &g, cudaStream_t st)
+{
+    CUtensorMap ta, tb, to, txb;
+    int rc = make_tmap(h, &ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.a, (uint64_t)g.M, (uint64_t)g.K,
+                       BM, BK);
     if (rc) return rc;
-    rc = make_tmap_2d(h, &tb, g.w, (uint64_t)g.N, (uint64_t)g.K, BN, BK);
+    rc = make_tmap(h, &tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.w, (uint64_t)g.N, (uint64_t)g.K,
+                   BN / 2, BK);
     if (rc) return rc;
-    // per device and cheap: set on every launch rather than caching in process-wide state
-    VG_CUDA_CHECK(h, cudaFuncSetAttribute(gemm_kernel<EPI>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)GEMM_SMEM));
-    GemmParams p;
-    p.bias = g.bias;
-    p.out = g.out;
-    p.M = g.M;
-    p.N = g.N;
-    p.K = g.K;
-    const int64_t tiles = ((g.M + BM - 1) / BM) * (g.N / BN);
-    const int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
-    const int kind = EPI == kEpiPatch ? VG_K_GEMM_PATCH
-                     : EPI == VG_EPI_BIAS_BF16 ? VG_K_GEMM_QKV
+    if (EPI == VG_EPI_BIAS_RESID_F32)
+        rc = make_tmap(h, &to, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.out, (uint64_t)g.M, (uint64_t)g.N,
+                       32, 32);
+    else
+        rc = make_tmap(h, &to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.out, (uint64_t)g.M,
+                       (uint64_t)g.N, 32, 64);
+    if (rc) return rc;
+    txb = to;
+    if (EPI == VG_EPI_BIAS_RESID_F32 && LNF) {
+        rc = make_tmap(h, &txb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.xb_out, (uint64_t)g.M,
+                       (uint64_t)g.N, 32, 64);
+        if (rc) return rc;
+    }
+    using Cfg = EpiCfg<EPI, LNF, RMODE>;
+    if ((rc = vg_set_smem_once(h, reinterpret_cast<const void *>(gemm2_kernel<EPI, LNF, RMODE, false>),
+                               Cfg::kSmem)))
+        return rc;
+    Params p{g.bias, g.colsum, g.stats, g.M, g.N, g.K};
+    const int64_t tiles = ((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / BN);
+    const int max_clusters = h->num_sms / 2;
+    const int clusters = (int)(tiles < max_clusters ? tiles : max_clusters);
+    const int kind = EPI == VG_EPI_BIAS_BF16 ? VG_K_GEMM_QKV
                      : EPI == VG_EPI_BIAS_QGELU_BF16 ? VG_K_GEMM_FC
                      : (g.K == kMlp ? VG_K_GEMM_PROJ : VG_K_GEMM_OUT);
-    // algorithmic FLOPs; the patch embedding is credited with the un-folded K = 3*16*16
-    const double kk = EPI == kEpiPatch ? 768.0 : (double)g.K;
-    VgProfScope prof(h, kind, 2.0 * (double)g.M * g.N * kk, st);
-    gemm_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ta, tb, p);
+    VgProfScope prof(h, kind, 2.0 * (double)g.M * g.N * (double)g.K, st);
+    gemm2_kernel<EPI, LNF, RMODE, false><<<2 * clusters, Cfg::kThreads, Cfg::kSmem, st>>>(ta, tb, to, txb, p);
     VG_LAUNCH_CHECK(h);
     return VG_OK;
 }
 
 }  // namespace
+
+// Patch embedding (model.py:223-229 with the preprocessing folded in):
+//   x[img][1 + p][:] = tiles[img][p][:] . W_eff^T + table[1 + p][:]
+// on the 2-CTA kernel: A is a 3-D map [img][196][256] tiled per image, the "residual" read is the
+// [197,768] table (L2 resident) and the store goes through a 3-D map [img][197][768] that clips the
+// rows beyond token 196.  The class-token row is written by ln_pre.
+int launch_gemm_patch(VgHandle *h, const GemmArgs &g, cudaStream_t st)
+{
+    if (g.M % kPatches != 0 || g.N != kWidth || g.K != kPatchK) {
+        VG_SET_ERR(h, "patch GEMM: unexpected shape M=%lld N=%d K=%d", (long long)g.M, g.N, g.K);
+        return VG_ESHAPE;
+    }
+    const uint64_t B = (uint64_t)(g.M / kPatches);
+    CUtensorMap ta, tb, to, ttab;
+    int rc = make_tmap3(h, &ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.a, kPatchK, kPatches, B, BK, BM);
+    if (rc) return rc;
+    rc = make_tmap(h, &tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.w, (uint64_t)g.N, (uint64_t)g.K, BN / 2, BK);
+    if (rc) return rc;
+    rc = make_tmap3(h, &to, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.out, kWidth, kTokens, B, 32, 32);
+    if (rc) return rc;
+    rc = make_tmap(h, &ttab, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.bias, kTokens, kWidth, 32, 32);
+    if (rc) return rc;
+    using Cfg = EpiCfg<VG_EPI_BIAS_RESID_F32, false, kWide>;
+    auto kern = gemm2_kernel<VG_EPI_BIAS_RESID_F32, false, kWide, true>;
+    if ((rc = vg_set_smem_once(h, reinterpret_cast<const void *>(kern), Cfg::kSmem))) return rc;
+    Params p{nullptr, nullptr, nullptr, g.M, g.N, g.K};
+    const int64_t tiles = (int64_t)B * (g.N / BN);
+    const int max_clusters = h->num_sms / 2;
+    const int clusters = (int)(tiles < max_clusters ? tiles : max_clusters);
+    // credited with the un-folded K = 3*16*16
+    VgProfScope prof(h, VG_K_GEMM_PATCH, 2.0 * (double)g.M * g.N * 768.0, st);
+    kern<<<2 * clusters, Cfg::kThreads, Cfg::kSmem, st>>>(ta, tb, to, ttab, p);
+    VG_LAUNCH_CHECK(h);
+    return VG_OK;
+}
 
 int launch_gemm(VgHandle *h, const GemmArgs &g, cudaStream_t st)
 {
@@ -293,22 +553,31 @@ int launch_gemm(VgHandle *h, const GemmArgs &g, cudaStream_t st)
         VG_SET_ERR(h, "gemm: operands must be 16-byte aligned");
         return VG_EINVAL;
     }
-    // production path: 2-CTA kernel with TMA-store epilogues (gemm_tcgen05_2cta.cu).  The single-CTA
-    // kernel below serves the patch embedding (row-remapping epilogue) and VG_GEMM_V1=1 (A/B runs).
-    const bool force_v1 = h->sw.gemm_v1;
-    if (g.epilogue == kEpiPatch && !force_v1) return launch_gemm_patch_2cta(h, g, st);
-    if (g.epilogue != kEpiPatch && !force_v1) return launch_gemm_2cta(h, g, st);
-    if (g.stats) {
-        VG_SET_ERR(h, "VG_GEMM_V1 has no LayerNorm-folded epilogues: set VG_LN_UNFUSED=1 as well");
+    if (g.epilogue == kEpiPatch) return launch_gemm_patch(h, g, st);
+    const bool lnf = g.stats != nullptr;
+    if (lnf && g.epilogue != VG_EPI_BIAS_RESID_F32 && !g.colsum) {
+        VG_SET_ERR(h, "gemm: LayerNorm-folded epilogue needs colsum");
+        return VG_EINVAL;
+    }
+    if (lnf && g.epilogue == VG_EPI_BIAS_RESID_F32 && (!g.xb_out || g.N != kWidth)) {
+        VG_SET_ERR(h, "gemm: fused residual epilogue needs xb_out and N = 768");
         return VG_EINVAL;
     }
     switch (g.epilogue) {
-        case VG_EPI_BIAS_BF16: return launch_gemm_t<VG_EPI_BIAS_BF16>(h, g, st);
-        case VG_EPI_BIAS_QGELU_BF16: return launch_gemm_t<VG_EPI_BIAS_QGELU_BF16>(h, g, st);
-        case VG_EPI_BIAS_RESID_F32: return launch_gemm_t<VG_EPI_BIAS_RESID_F32>(h, g, st);
-        case kEpiPatch: return launch_gemm_t<kEpiPatch>(h, g, st);
+        case VG_EPI_BIAS_BF16:
+            return lnf ? launch_t<VG_EPI_BIAS_BF16, true>(h, g, st) : launch_t<VG_EPI_BIAS_BF16, false>(h, g, st);
+        case VG_EPI_BIAS_QGELU_BF16:
+            return lnf ? launch_t<VG_EPI_BIAS_QGELU_BF16, true>(h, g, st)
+                       : launch_t<VG_EPI_BIAS_QGELU_BF16, false>(h, g, st);
+        case VG_EPI_BIAS_RESID_F32:
+            if (lnf && g.K <= kWidth && !h->sw.gemm_narrow)   // out-proj: epilogue bound -> 8 warps
+                return launch_t<VG_EPI_BIAS_RESID_F32, true, kWide>(h, g, st);
+            if (lnf && !h->sw.gemm_narrow)                    // c_proj: tensor bound -> 5-stage ring
+                return launch_t<VG_EPI_BIAS_RESID_F32, true, kDeep>(h, g, st);
+            return lnf ? launch_t<VG_EPI_BIAS_RESID_F32, true>(h, g, st)
+                       : launch_t<VG_EPI_BIAS_RESID_F32, false>(h, g, st);
     }
-    VG_SET_ERR(h, "gemm: unknown epilogue %d", g.epilogue);
+    VG_SET_ERR(h, "gemm: unsupported epilogue %d", g.epilogue);
     return VG_EINVAL;
 }
 

@@ -7,14 +7,30 @@
 //   3-D grid scatter-max          src/utils/mv_utils.py:120-127  (torch_scatter reduce="max")
 //   5x5 max-pool, 3x3 Gaussian,   src/utils/mv_utils.py:30-37    (GridToImage.forward)
 //   depth max, /max, 1-x
-//   bilinear 110->224, uint8      src/vilgod/zero_shot_detector.py:405-409
+//   bilinear (R-2)->224, uint8    src/vilgod/zero_shot_detector.py:405-409
 //   ToTensor / Normalize          third_party/CLIP/clip/clip.py:79-86 (folded into the patch-embed
-//                                 weights; the kernel emits the integer pixel 0..255 as bf16)
+//                                 weights; the kernel emits the integer pixel 0..255 as bf16 / fp16)
 //
 // Data flow: points are read from HBM (L2 for views > 0), every intermediate (one depth slice of
 // the grid, the running depth-max image, the horizontally interpolated rows) lives in shared
-// memory, and the only HBM writes are the patch-major bf16 tile (100,352 B per image) and, on
-// request, the uint8 image.  Algorithmic bytes per cluster: 12 N + V * 224*224*2.
+// memory, and the only HBM writes are the patch-major tile (100,352 B per image) and, on request,
+// the uint8 image.  Algorithmic bytes per cluster: 12 N + V * 224*224*2.
+//
+// Two ways through the per-slice stencil, chosen per image, identical results:
+//   stamp  (N <= 1024, 87 % of a Waymo-shaped mix): the quantised points are counting-sorted by depth
+//          slice; per occupied slice the 5x5 max-pool is applied AT SCATTER TIME (each point stamps its
+//          5x5 footprint with shared-memory atomicMax: max-pool of a sparse grid is the union of the
+//          footprints), and the 3x3 Gaussian + depth max run only over the slice's bounding box with
+//          the work flattened over all lanes.  Nothing outside the bounding box is touched.
+//   dense  (larger clusters, and whenever the raw grid is requested as a debug tap): scatter-max of
+//          the raw cells, then a row-streaming separable 5x5 max + Gaussian with register rings.
+// The emit (bilinear, uint8 quantisation, patch-major tile) is restricted to the output rows AND
+// column groups whose four source pixels can differ from background; everything else is copied from
+// a precomputed background tile.
+//
+// R = 112 (reference configuration): grid slice + image in shared memory, two CTAs per SM.
+// R = 224 (BASELINE.json configs[3] sweep): the slice alone is 196 KB, so the running image lives
+// in a per-SM scratch in global memory (L2 resident) and one CTA runs per SM.
 //
 // Numerics contract (tests/test_projection_gpu.py): occupancy masks and scatter winners bit-exact
 // against the oracle; every fp32 operation up to the scatter is a single IEEE-rounded operation in
@@ -26,17 +42,16 @@
 namespace vg {
 namespace {
 
-constexpr int R = 112;          // grid resolution
 constexpr int D = 8;            // depth slices
 constexpr int S = 224;          // output image size
-constexpr int Q = R - 2;        // densified image size (110)
 constexpr int NT = 512;         // threads per CTA
 constexpr int NW = NT / 32;     // 16 warps
-constexpr int CH = 7;           // rows per warp chunk in the stencil passes (16 x 7 = 112)
-constexpr int HI_ROWS = 56;     // source rows whose horizontal interpolation fits the grid buffer
-constexpr int POOL = 65536 - 1408;   // pooled points per resident CTA (N <= 65,536 never recomputes)
+constexpr int CH = 7;           // max rows per warp chunk in the dense stencil pass
+constexpr int CAP = 1408;       // points whose quantised (x, y, slice, value) are cached in smem
+constexpr int POOL = 65536 - CAP;    // pooled points per resident CTA (N <= 65,536 never recomputes)
 constexpr int kSpillPerSm = 2;  // resident CTAs per SM (shared memory bound)
-constexpr int CAP = 1408;       // points whose quantised (cell, slice, value) are cached in smem
+constexpr int STAMP_N = 2 * NT; // largest cluster that takes the stamp path (two points per thread)
+constexpr int NG = S / 8;       // 8-pixel output groups per row (28)
 
 // bilinear index / weight table (identical for rows and columns: square images) and the image a
 // cluster-free region produces, both built once per handle by projection_tables_kernel
@@ -55,29 +70,42 @@ struct ProjParams {
     const ProjTables *tab;
     uint2 *spill;          // [slots][POOL] quantised points beyond the shared-memory cache
     int *spill_flags;      // [slots] 0 = free
+    float *img_scratch;    // R = 224: [nsmid][Q*R] running depth-max image of the CTA on that SM
     int32_t spill_sms;     // SM ids covered by the spill pool (%nsmid)
     int32_t C, V;
     float rot[VG_MAX_VIEWS * 9];
     float gauss[9];
     float obj_ratio, depth_bias, one_plus_bias;
-    int32_t rotate_mode;
+    int32_t rotate_mode, div_mode;
     op_t *tiles;
     uint8_t *u8;
+    int32_t u8_first_only; // u8 is [C,S,S] and receives view 0 only
     int32_t *status;
     float *dbg_grid;
     float *dbg_dens;
 };
 
-struct Smem {
-    float G[R * R];        // one depth slice of the grid / pooled slice / HI rows (56 x 224)
-    float IMG[R * R];      // running max over depth of the smoothed slices, row stride R
-    uint2 cache[CAP];      // per point: (cell | slice << 16, value bits)
-    float red[6 * NW];
-    float norm[4];         // pcent xyz, prange
+template <int R> struct Geo {
+    static constexpr int Q = R - 2;             // densified image size (110 / 222)
+    static constexpr int NS = R / 4;            // float4 strips per grid row
+    static constexpr int MW = (R + 31) / 32;    // words of a row / column occupancy mask
+    static constexpr int NSEG = R / 112;        // 28-strip segments per row in the dense pass
+    static constexpr int HI_ROWS = R * R / S;   // source rows whose horizontal interpolation fits G
+    static constexpr bool kImgSmem = R == 112;
+};
+
+template <int R> struct Smem {
+    float G[R * R];        // one depth slice of the grid / pooled slice / horizontally interpolated rows
+    float IMG[Geo<R>::kImgSmem ? (R - 2) * R : 4];   // running max over depth of the smoothed slices
+    uint2 cache[CAP];      // per point: (x | y << 8 | slice << 16, value bits)
+    unsigned ext[6];       // order-preserving keys of max xyz / min xyz
+    unsigned rowmask[D][Geo<R>::MW], colmask[D][Geo<R>::MW];   // occupied grid rows / columns per slice
+    int ylo[D], yhi[D], xlo[D], xhi[D];
+    int cnt[D];            // points per slice (stamp path: counting sort)
+    int ulo, uhi, vlo, vhi;   // rows / columns of IMG any slice can touch
+    int oy_lo, oy_hi, g_lo, g_hi;   // output rows / 8-pixel column groups that can differ from background
+    float red[NW];
     float mx;
-    unsigned rowmask[D][4];   // occupied grid rows per depth slice
-    int ylo[D], yhi[D];
-    int ulo, uhi;          // rows of IMG any slice can touch
     unsigned mask;         // occupied depth slices
     int degenerate;
     int spill_slot;        // global point pool of this CTA (clusters above CAP points), -1 = none
@@ -119,6 +147,17 @@ __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
     return r;
 }
 
+// order-preserving float <-> unsigned keys (shared-memory atomicMax / atomicMin on floats of any sign)
+__device__ __forceinline__ unsigned f2key(float f)
+{
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(unsigned k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
 __device__ __forceinline__ void rotate_point(const float *__restrict__ p, const float *rm,
                                              bool fused, float &qx, float &qy, float &qz)
 {
@@ -154,6 +193,7 @@ struct Quant {
 };
 
 // mv_utils.py:101-118, one rounded op per operator
+template <int R>
 __device__ __forceinline__ void quantise(float qx, float qy, float qz, const Quant &n,
                                          const ProjParams &P, int &X, int &Y, int &zi, float &val)
 {
@@ -165,7 +205,11 @@ __device__ __forceinline__ void quantise(float qx, float qy, float qz, const Qua
     const float fx = __fmul_rn(__fmul_rn(__fadd_rn(ux, 1.0f), 0.5f), (float)R);
     const float fy = __fmul_rn(__fmul_rn(__fadd_rn(uy, 1.0f), 0.5f), (float)R);
     float fz = __fadd_rn(__fmul_rn(__fadd_rn(uz, 1.0f), 0.5f), P.depth_bias);
-    fz = __fmul_rn(div_rn(fz, P.one_plus_bias, n.rc_opb, n.slow), (float)(D - 2));
+    // `/ (1 + depth_bias)`: true division (torch-CPU, the oracle) or multiplication by the rounded
+    // reciprocal (what torch-CUDA does for a division by a Python scalar), VgConfig.div_mode
+    fz = P.div_mode == VG_DIV_RECIPROCAL ? __fmul_rn(fz, n.rc_opb)
+                                         : div_rn(fz, P.one_plus_bias, n.rc_opb, n.slow);
+    fz = __fmul_rn(fz, (float)(D - 2));
     X = (int)fminf(fmaxf(ceilf(fx), 1.0f), (float)(R - 2));
     Y = (int)fminf(fmaxf(ceilf(fy), 1.0f), (float)(R - 2));
     zi = min(max((int)ceilf(fz), 0), D - 1);
@@ -176,12 +220,6 @@ __device__ __forceinline__ float warp_max(float v)
 {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-__device__ __forceinline__ float warp_min(float v)
-{
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
 __device__ __forceinline__ float max3f(float a, float b, float c)
@@ -196,12 +234,12 @@ __device__ __forceinline__ float4 max4(float4 a, float4 b)
 }
 
 // bilinear source index / weights, torch area_pixel_compute_source_index(align_corners=True)
-__device__ __forceinline__ void lin_idx(int dst, int &i0, float &l0, float &l1)
+__device__ __forceinline__ void lin_idx(int Qn, int dst, int &i0, float &l0, float &l1)
 {
-    const float scale = __fdiv_rn((float)(Q - 1), (float)(S - 1));
+    const float scale = __fdiv_rn((float)(Qn - 1), (float)(S - 1));
     const float src = __fmul_rn(scale, (float)dst);
     int a = (int)floorf(src);
-    a = min(a, Q - 1);
+    a = min(a, Qn - 1);
     float lam = __fsub_rn(src, (float)a);
     lam = fminf(fmaxf(lam, 0.0f), 1.0f);
     i0 = a;
@@ -217,7 +255,7 @@ __device__ __forceinline__ float quant255(float o)
     return __fsub_rn(t, 8388608.0f);
 }
 
-__global__ void projection_tables_kernel(ProjTables *t)
+__global__ void projection_tables_kernel(ProjTables *t, int Qn)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     if (tid == 0) {
@@ -227,7 +265,7 @@ __global__ void projection_tables_kernel(ProjTables *t)
     }
     if (tid < S) {
         int i0; float l0, l1;
-        lin_idx(tid, i0, l0, l1);
+        lin_idx(Qn, tid, i0, l0, l1);
         t->i0[tid] = i0; t->l0[tid] = l0; t->l1[tid] = l1;
     }
     // the image of an all-background (1.0) neighbourhood: HI = fma(1, lw0, 1*lw1), then the
@@ -235,8 +273,8 @@ __global__ void projection_tables_kernel(ProjTables *t)
     for (int px = tid; px < S * S; px += gridDim.x * blockDim.x) {
         const int oy = px / S, ox = px - oy * S;
         int x0, y0; float lw0, lw1, lh0, lh1;
-        lin_idx(ox, x0, lw0, lw1);
-        lin_idx(oy, y0, lh0, lh1);
+        lin_idx(Qn, ox, x0, lw0, lw1);
+        lin_idx(Qn, oy, y0, lh0, lh1);
         const float c = __fmaf_rn(1.0f, lw0, __fmul_rn(1.0f, lw1));
         const float v = quant255(__fmaf_rn(c, lh0, __fmul_rn(c, lh1)));
         reinterpret_cast<uint8_t *>(t->bg_u8)[px] = (uint8_t)v;
@@ -245,10 +283,52 @@ __global__ void projection_tables_kernel(ProjTables *t)
     }
 }
 
-__global__ void __launch_bounds__(NT, 2) projection_kernel(const ProjParams P)
+// running depth-max image: shared memory (R = 112) or the per-SM global scratch (R = 224; .cg so
+// that what another thread of the CTA wrote before the last barrier is what this load returns)
+template <bool SMEM> __device__ __forceinline__ float4 img_ld4(const float *p)
 {
+    if (SMEM) return *reinterpret_cast<const float4 *>(p);
+    return __ldcg(reinterpret_cast<const float4 *>(p));
+}
+template <bool SMEM> __device__ __forceinline__ void img_st4(float *p, float4 v)
+{
+    if (SMEM) *reinterpret_cast<float4 *>(p) = v;
+    else __stcg(reinterpret_cast<float4 *>(p), v);
+}
+template <bool SMEM> __device__ __forceinline__ float img_ld(const float *p)
+{
+    if (SMEM) return *p;
+    return __ldcg(p);
+}
+
+// 3x3 Gaussian (zero padding) of three pooled rows as a row-major FMA chain -- the summation order
+// the oracle uses -- for the four pixels of one strip; t*[0] / t*[5] are the neighbouring columns
+__device__ __forceinline__ void gauss4(const float (&w)[9], const float (&ta)[6], const float (&tb)[6],
+                                       const float (&tc)[6], float (&o)[4])
+{
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float acc = __fmul_rn(w[0], ta[j]);
+        acc = __fmaf_rn(w[1], ta[j + 1], acc);
+        acc = __fmaf_rn(w[2], ta[j + 2], acc);
+        acc = __fmaf_rn(w[3], tb[j], acc);
+        acc = __fmaf_rn(w[4], tb[j + 1], acc);
+        acc = __fmaf_rn(w[5], tb[j + 2], acc);
+        acc = __fmaf_rn(w[6], tc[j], acc);
+        acc = __fmaf_rn(w[7], tc[j + 1], acc);
+        acc = __fmaf_rn(w[8], tc[j + 2], acc);
+        o[j] = acc;
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(NT, R == 112 ? 2 : 1) projection_kernel(const ProjParams P)
+{
+    using GE = Geo<R>;
+    constexpr int Q = GE::Q, NS = GE::NS, MW = GE::MW;
+    constexpr bool ISM = GE::kImgSmem;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    Smem<R> &sm = *reinterpret_cast<Smem<R> *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x;
     const int c = b / P.V, v = b - c * P.V;
@@ -258,73 +338,88 @@ __global__ void __launch_bounds__(NT, 2) projection_kernel(const ProjParams P)
     const float *rm = P.rot + 9 * v;
     const bool fused = P.rotate_mode == VG_ROTATE_FUSED ||
                        (P.rotate_mode == VG_ROTATE_TORCH_CPU && 9 * (long long)n >= 400);
+    float *IMG = sm.IMG;
+    if (!ISM) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        IMG = P.img_scratch + (size_t)smid * Q * R;      // one resident CTA per SM at R = 224
+    }
 
     // ---- phase 1: per-axis min / max of the rotated points --------------------------------------
-    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY;
-    float mn0 = INFINITY, mn1 = INFINITY, mn2 = INFINITY;
-    bool finite = true;
-    for (int i = tid; i < n; i += NT) {
-        float qx, qy, qz;
-        rotate_point(pts + 3 * i, rm, fused, qx, qy, qz);
-        finite = finite && isfinite(qx) && isfinite(qy) && isfinite(qz);
-        mx0 = fmaxf(mx0, qx); mx1 = fmaxf(mx1, qy); mx2 = fmaxf(mx2, qz);
-        mn0 = fminf(mn0, qx); mn1 = fminf(mn1, qy); mn2 = fminf(mn2, qz);
+    {
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY;
+        float mn0 = INFINITY, mn1 = INFINITY, mn2 = INFINITY;
+        bool finite = true;
+        for (int i = tid; i < n; i += NT) {
+            float qx, qy, qz;
+            rotate_point(pts + 3 * i, rm, fused, qx, qy, qz);
+            finite = finite && isfinite(qx) && isfinite(qy) && isfinite(qz);
+            mx0 = fmaxf(mx0, qx); mx1 = fmaxf(mx1, qy); mx2 = fmaxf(mx2, qz);
+            mn0 = fminf(mn0, qx); mn1 = fminf(mn1, qy); mn2 = fminf(mn2, qz);
+        }
+        if (tid < 6) sm.ext[tid] = tid < 3 ? 0u : 0xffffffffu;
+        if (tid < D * MW) { (&sm.rowmask[0][0])[tid] = 0u; (&sm.colmask[0][0])[tid] = 0u; }
+        if (tid < D) sm.cnt[tid] = 0;
+        if (tid == 0) {
+            sm.mask = 0u; sm.degenerate = 0;
+            sm.ulo = Q; sm.uhi = -1; sm.vlo = Q; sm.vhi = -1;
+            sm.oy_lo = S; sm.oy_hi = -1; sm.g_lo = NG; sm.g_hi = -1;
+        }
+        const unsigned k0 = __reduce_max_sync(0xffffffffu, f2key(mx0));
+        const unsigned k1 = __reduce_max_sync(0xffffffffu, f2key(mx1));
+        const unsigned k2 = __reduce_max_sync(0xffffffffu, f2key(mx2));
+        const unsigned k3 = __reduce_min_sync(0xffffffffu, f2key(mn0));
+        const unsigned k4 = __reduce_min_sync(0xffffffffu, f2key(mn1));
+        const unsigned k5 = __reduce_min_sync(0xffffffffu, f2key(mn2));
+        const bool all_finite = __all_sync(0xffffffffu, finite);
+        __syncthreads();
+        if (lane == 0) {
+            atomicMax(&sm.ext[0], k0); atomicMax(&sm.ext[1], k1); atomicMax(&sm.ext[2], k2);
+            atomicMin(&sm.ext[3], k3); atomicMin(&sm.ext[4], k4); atomicMin(&sm.ext[5], k5);
+            if (!all_finite) sm.degenerate = 1;
+        }
+        __syncthreads();
     }
-    mx0 = warp_max(mx0); mx1 = warp_max(mx1); mx2 = warp_max(mx2);
-    mn0 = warp_min(mn0); mn1 = warp_min(mn1); mn2 = warp_min(mn2);
-    const bool all_finite = __all_sync(0xffffffffu, finite);
-    if (tid < D * 4) (&sm.rowmask[0][0])[tid] = 0u;
-    if (tid == 0) { sm.mask = 0u; sm.degenerate = 0; }
-    __syncthreads();
-    if (lane == 0) {
-        sm.red[warp] = mx0; sm.red[NW + warp] = mx1; sm.red[2 * NW + warp] = mx2;
-        sm.red[3 * NW + warp] = mn0; sm.red[4 * NW + warp] = mn1; sm.red[5 * NW + warp] = mn2;
-        if (!all_finite) sm.degenerate = 1;
-    }
-    __syncthreads();
-    if (warp == 0) {
+    Quant qn;
+    {
         float a[6];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            float t = lane < NW ? sm.red[k * NW + lane] : (k < 3 ? -INFINITY : INFINITY);
-            a[k] = k < 3 ? warp_max(t) : warp_min(t);
-        }
-        if (lane == 0) {
-            sm.norm[0] = __fmul_rn(__fadd_rn(a[0], a[3]), 0.5f);
-            sm.norm[1] = __fmul_rn(__fadd_rn(a[1], a[4]), 0.5f);
-            sm.norm[2] = __fmul_rn(__fadd_rn(a[2], a[5]), 0.5f);
-            const float pr = fmaxf(fmaxf(__fsub_rn(a[0], a[3]), __fsub_rn(a[1], a[4])),
-                                   __fsub_rn(a[2], a[5]));
-            sm.norm[3] = pr;
-            if (n <= 0 || !(pr > 0.0f) || !isfinite(pr)) sm.degenerate = 1;
-        }
+        for (int k = 0; k < 6; ++k) a[k] = key2f(sm.ext[k]);
+        qn.cx = __fmul_rn(__fadd_rn(a[0], a[3]), 0.5f);
+        qn.cy = __fmul_rn(__fadd_rn(a[1], a[4]), 0.5f);
+        qn.cz = __fmul_rn(__fadd_rn(a[2], a[5]), 0.5f);
+        qn.pr = fmaxf(fmaxf(__fsub_rn(a[0], a[3]), __fsub_rn(a[1], a[4])), __fsub_rn(a[2], a[5]));
     }
-    __syncthreads();
-    if (sm.degenerate) {   // defined behaviour where the reference yields NaN: zero tile + status
-        if (P.tiles) {
-            uint4 *t = reinterpret_cast<uint4 *>(P.tiles + (size_t)b * VG_TILE_ELEMS);
+    op_t *tile = P.tiles ? P.tiles + (size_t)b * VG_TILE_ELEMS : nullptr;
+    uint8_t *u8 = nullptr;
+    if (P.u8) {
+        if (!P.u8_first_only) u8 = P.u8 + (size_t)b * S * S;
+        else if (v == 0) u8 = P.u8 + (size_t)c * S * S;
+    }
+    if (sm.degenerate || n <= 0 || !(qn.pr > 0.0f) || !isfinite(qn.pr)) {
+        // defined behaviour where the reference yields NaN: zero tile + status
+        if (tile) {
+            uint4 *t = reinterpret_cast<uint4 *>(tile);
             for (int i = tid; i < VG_TILE_ELEMS / 8; i += NT) t[i] = make_uint4(0, 0, 0, 0);
         }
-        if (P.u8) {
-            uint4 *t = reinterpret_cast<uint4 *>(P.u8 + (size_t)b * S * S);
+        if (u8) {
+            uint4 *t = reinterpret_cast<uint4 *>(u8);
             for (int i = tid; i < S * S / 16; i += NT) t[i] = make_uint4(0, 0, 0, 0);
         }
         if (P.status && v == 0 && tid == 0) P.status[c] = VG_EDEGENERATE;
         return;
     }
     if (P.status && v == 0 && tid == 0) P.status[c] = VG_OK;
-    for (int i = tid; i < R * R / 4; i += NT)       // the one clear of the grid buffer (phase 3)
-        reinterpret_cast<float4 *>(sm.G)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    Quant qn;
-    qn.cx = sm.norm[0]; qn.cy = sm.norm[1]; qn.cz = sm.norm[2]; qn.pr = sm.norm[3];
     qn.rc_pr = __frcp_rn(qn.pr);
     qn.rc_opb = __frcp_rn(P.one_plus_bias);
     qn.slow = !(qn.pr > 1e-18f && qn.pr < 1e18f);
 
-    // ---- phase 2: quantise once; occupied slices and rows; cache (cell, slice, value) ------------
-    // The first CAP points keep their quantised (cell, slice, value) in shared memory and are replayed
-    // per slice.  Points beyond that go to a private pool in global memory (L2 resident; one per
+    // ---- phase 2: quantise once; occupied slices, rows and columns; cache (x, y, slice, value) ----
+    // stamp path: every point stays in registers until the per-slice counts are known and is then
+    // written to its slot of the slice-sorted cache.  dense path: the first CAP points go to the
+    // cache in point order, the rest to a private pool in global memory (L2 resident; one per
     // resident CTA, claimed per SM), so no point is rotated and quantised more than once per view.
+    const bool stamp = n <= STAMP_N && !P.dbg_grid;
     const bool big = n > CAP;
     if (big && tid == 0) {
         unsigned smid;
@@ -342,226 +437,364 @@ __global__ void __launch_bounds__(NT, 2) projection_kernel(const ProjParams P)
     const int npool = pool ? min(n - CAP, POOL) : 0;
     {
         unsigned m = 0u;
-        for (int i = tid; i < n; i += NT) {
+        uint2 held[2];
+        int hz[2] = {-1, -1}, hr[2] = {0, 0};
+        auto one = [&](int i, int k) {
             float qx, qy, qz, val; int X, Y, zi;
             rotate_point(pts + 3 * i, rm, fused, qx, qy, qz);
-            quantise(qx, qy, qz, qn, P, X, Y, zi, val);
+            quantise<R>(qx, qy, qz, qn, P, X, Y, zi, val);
             m |= 1u << zi;
             atomicOr(&sm.rowmask[zi][Y >> 5], 1u << (Y & 31));
-            const uint2 e = make_uint2((unsigned)(Y * R + X) | ((unsigned)zi << 16), __float_as_uint(val));
-            if (i < CAP) sm.cache[i] = e;
-            else if (i - CAP < npool) __stcg(pool + (i - CAP), e);
+            atomicOr(&sm.colmask[zi][X >> 5], 1u << (X & 31));
+            const uint2 e = make_uint2((unsigned)X | ((unsigned)Y << 8) | ((unsigned)zi << 16),
+                                       __float_as_uint(val));
+            if (stamp) {
+                held[k] = e;
+                hz[k] = zi;
+                hr[k] = atomicAdd(&sm.cnt[zi], 1);
+            } else if (i < CAP) {
+                sm.cache[i] = e;
+            } else if (i - CAP < npool) {
+                __stcg(pool + (i - CAP), e);
+            }
+        };
+        if (stamp) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                if (tid + k * NT < n) one(tid + k * NT, k);
+        } else {
+            for (int i = tid; i < n; i += NT) one(i, 0);
         }
         m = __reduce_or_sync(0xffffffffu, m);
         if (lane == 0 && m) atomicOr(&sm.mask, m);
+        __syncthreads();
+        if (stamp) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                if (hz[k] >= 0) {
+                    int base = 0;
+                    for (int d = 0; d < hz[k]; ++d) base += sm.cnt[d];
+                    sm.cache[base + hr[k]] = held[k];
+                }
+        }
     }
-    __syncthreads();
-    if (tid < D) {
+    if (tid < 2 * D) {     // occupied row / column range per slice, and their union in IMG terms
+        const int d = tid >> 1;
+        const bool rows = (tid & 1) == 0;
         int lo = R, hi = -1;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            const unsigned bits = sm.rowmask[tid][w];
+        for (int w = 0; w < MW; ++w) {
+            const unsigned bits = rows ? sm.rowmask[d][w] : sm.colmask[d][w];
             if (bits) {
                 lo = min(lo, 32 * w + __ffs(bits) - 1);
                 hi = max(hi, 32 * w + 31 - __clz(bits));
             }
         }
-        sm.ylo[tid] = lo; sm.yhi[tid] = hi;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        int ulo = Q, uhi = -1;
-        for (int d = 0; d < D; ++d)
-            if (sm.yhi[d] >= 0) {
-                ulo = min(ulo, max(sm.ylo[d] - 4, 0));
-                uhi = max(uhi, min(sm.yhi[d] + 2, Q - 1));
-            }
-        sm.ulo = ulo; sm.uhi = uhi;
+        if (rows) { sm.ylo[d] = lo; sm.yhi[d] = hi; } else { sm.xlo[d] = lo; sm.xhi[d] = hi; }
+        if (hi >= 0) {
+            atomicMin(rows ? &sm.ulo : &sm.vlo, max(lo - 4, 0));
+            atomicMax(rows ? &sm.uhi : &sm.vhi, min(hi + 2, Q - 1));
+        }
     }
     __syncthreads();
     const unsigned mask = sm.mask;
-    const int ulo = sm.ulo, uhi = sm.uhi;                 // IMG rows any slice writes
-    const int nlo = max(ulo - 1, 0), nhi = min(uhi + 1, Q - 1);   // rows the emit may read
-    // IMG starts at 0 == max over the empty slices (their smoothed image is identically 0)
-    for (int i = tid; i < (nhi - nlo + 1) * (R / 4); i += NT)
-        reinterpret_cast<float4 *>(sm.IMG + nlo * R)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int ulo = sm.ulo, uhi = sm.uhi, vlo = sm.vlo, vhi = sm.vhi;   // IMG cells any slice writes
+    const int nlo = max(ulo - 1, 0), nhi = min(uhi + 1, Q - 1);          // rows the emit may read
+    // strips the emit may read: an 8-pixel output group is computed as soon as one of its pixels has a
+    // source column in [vlo, vhi], and its other pixels reach up to kColSpan source columns further
+    constexpr int kColSpan = (7 * (Q - 1)) / (S - 1) + 2;
+    const int ns_lo = max(vlo - kColSpan, 0) >> 2, ns_hi = min(vhi + kColSpan, Q - 1) >> 2;
+    const ProjTables *__restrict__ tab = P.tab;
+    // output rows / 8-pixel column groups with at least one source pixel inside the touched region
+    if (tid < S) {
+        int y0; float t0, t1;
+        lin_idx(Q, tid, y0, t0, t1);
+        const int y1 = y0 + (y0 < Q - 1 ? 1 : 0);
+        if (!(y1 < ulo || y0 > uhi)) { atomicMin(&sm.oy_lo, tid); atomicMax(&sm.oy_hi, tid); }
+    } else if (tid < S + NG) {
+        const int g = tid - S;
+        const int xa = __ldg(&tab->i0[8 * g]);
+        int xb = __ldg(&tab->i0[8 * g + 7]);
+        xb += xb < Q - 1 ? 1 : 0;
+        if (!(xb < vlo || xa > vhi)) { atomicMin(&sm.g_lo, g); atomicMax(&sm.g_hi, g); }
+    }
+    // IMG starts at 0 == max over the empty slices (their smoothed image is identically 0); the
+    // dense pass writes whole rows, the stamp pass only inside [ns_lo, ns_hi]
+    {
+        const int s0 = stamp ? ns_lo : 0, s1 = stamp ? ns_hi : NS - 1;
+        for (int r = nlo + warp; r <= nhi; r += NW)
+            for (int s = s0 + lane; s <= s1; s += 32)
+                img_st4<ISM>(IMG + r * R + 4 * s, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+    if (!stamp)       // dense path: the one clear of the grid buffer
+        for (int i = tid; i < R * R / 4; i += NT)
+            reinterpret_cast<float4 *>(sm.G)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    const int oy_lo = sm.oy_lo, oy_hi = sm.oy_hi, g_lo = sm.g_lo, g_hi = sm.g_hi;
+
+    // ---- background: every output group outside the active rows x groups is a copy of the
+    // precomputed background tile; issued now so that the stores drain behind the stencil work ----
+    {
+#pragma unroll 4
+        for (int idx = tid; idx < S * NG; idx += NT) {
+            const int oy = idx / NG, g = idx - oy * NG;
+            if (oy >= oy_lo && oy <= oy_hi && g >= g_lo && g <= g_hi) continue;
+            const int patch = (oy >> 4) * 14 + (g >> 1);
+            const int inner = (oy & 15) * 16 + (g & 1) * 8;
+            if (tile)
+                *reinterpret_cast<uint4 *>(tile + patch * 256 + inner) =
+                    __ldg(&tab->bg_tile[(patch * 256 + inner) >> 3]);
+            if (u8)
+                *reinterpret_cast<uint2 *>(u8 + oy * S + 8 * g) = __ldg(&tab->bg_u8[(oy * S + 8 * g) >> 3]);
+        }
+    }
 
     float w[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) w[k] = P.gauss[k];
 
     // ---- phase 3: per occupied slice: scatter-max, 5x5 max-pool, 3x3 Gaussian, depth max --------
-    // The grid buffer is cleared ONCE.  Slices are visited in increasing depth and a point of slice d
-    // carries a value in (d-1, d], so whatever lower slices left behind is <= d-1: scatter-max simply
-    // overwrites it, and after pooling (max commutes with the monotone cut) everything <= d-1 is cut
-    // to the 0 an empty cell holds.  Only slices whose values can tie with a lower one (0/1: both 1.0,
-    // 7: 6.0 like the top of slice 6 -- both only reachable through rounding) clear again.
-    // Per slice that leaves two block barriers: scatter | fused stencil pass.  In the fused pass a warp
-    // owns a chunk of smoothed rows and streams the raw rows it needs through registers: horizontal
-    // 5-max (shuffles), vertical 5-max over a ring of 5 rows, cut, 3x3 Gaussian over a ring of 3
-    // pooled rows, running depth max into IMG.  Rows outside [ylo, yhi] hold no point of the slice and
-    // are not even loaded.
-    bool dirty = false;       // G holds values of a lower slice
-    for (int d = 0; d < D; ++d) {
-        if (!((mask >> d) & 1u)) {
-            if (P.dbg_grid) {
-                float *g = P.dbg_grid + ((size_t)b * D + d) * R * R;
-                for (int i = tid; i < R * R; i += NT) g[i] = 0.0f;
-            }
-            continue;
-        }
-        const int ylo = sm.ylo[d], yhi = sm.yhi[d];
-        float thr = 0.0f;
-        if (dirty) {
-            if (d >= 2 && d <= D - 2) {
-                thr = (float)(d - 1);
-            } else {
-                for (int i = tid; i < R * R / 4; i += NT)
-                    reinterpret_cast<float4 *>(sm.G)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                __syncthreads();
-            }
-        }
-        dirty = true;
-        {
-            const int ncache = min(n, CAP);
-            for (int i = tid; i < ncache; i += NT) {
-                const uint2 e = sm.cache[i];
-                // all values are positive floats: integer order == float order
-                if ((int)(e.x >> 16) == d)
-                    atomicMax(reinterpret_cast<int *>(sm.G) + (e.x & 0xffffu), (int)e.y);
-            }
-            // pooled points: 4 independent L2 loads in flight per thread
-            for (int i0 = tid; i0 < npool; i0 += 4 * NT) {
-                uint2 e[4];
+    if (stamp) {
+        int base = 0;
+        for (int d = 0; d < D; ++d) {
+            if (!((mask >> d) & 1u)) continue;
+            const int cnt = sm.cnt[d];
+            const int ylo = sm.ylo[d], yhi = sm.yhi[d], xlo = sm.xlo[d], xhi = sm.xhi[d];
+            const int gy0 = max(ylo - 4, 0), gy1 = min(yhi + 2, Q - 1);       // smoothed rows
+            const int gs_lo = max(xlo - 4, 0) >> 2, gs_hi = min(xhi + 2, Q - 1) >> 2;   // and strips
+            const int py0 = max(ylo - 3, 0), py1 = min(yhi + 1, Q - 1);       // rows a stamp reaches
+            const int ns = gs_hi - gs_lo + 1;
+            // clear exactly the pooled cells this slice's Gaussian reads
+            for (int r = py0 + warp; r <= py1; r += NW)
+                for (int s = gs_lo + lane; s <= gs_hi; s += 32)
+                    reinterpret_cast<float4 *>(sm.G + r * R)[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncthreads();
+            // stamp: one item = one row of one point's 5x5 footprint.  Pooled pixel (q, x) covers raw
+            // cells (q-1..q+3, x-1..x+3), so a point at (Y, X) reaches q in [Y-3, Y+1], x in [X-3, X+1].
+            // All values are positive floats: integer order == float order.
+            for (int item = tid; item < 5 * cnt; item += NT) {
+                const int p = item / 5, dy = item - 5 * p;
+                const uint2 e = sm.cache[base + p];
+                const int X = (int)(e.x & 255u), Y = (int)((e.x >> 8) & 255u);
+                const int q = Y - 3 + dy;
+                if (q < 0 || q > Q - 1) continue;
+                int *row = reinterpret_cast<int *>(sm.G) + q * R;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    e[k] = i0 + k * NT < npool ? __ldcg(pool + i0 + k * NT) : make_uint2(0xffffffffu, 0u);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if ((int)(e[k].x >> 16) == d)
-                        atomicMax(reinterpret_cast<int *>(sm.G) + (e[k].x & 0xffffu), (int)e[k].y);
+                for (int dx = 0; dx < 5; ++dx) {
+                    const int x = X - 3 + dx;
+                    if (x >= 0 && x <= Q - 1) atomicMax(row + x, (int)e.y);
+                }
             }
-            // beyond the pool (N > CAP + POOL), or every pool of this SM taken (cannot happen at two
-            // resident CTAs per SM): rotate and quantise again
-            for (int i = CAP + npool + tid; i < n; i += NT) {
-                float qx, qy, qz, val; int X, Y, zi;
-                rotate_point(pts + 3 * i, rm, fused, qx, qy, qz);
-                quantise(qx, qy, qz, qn, P, X, Y, zi, val);
-                if (zi == d) atomicMax(reinterpret_cast<int *>(sm.G) + Y * R + X, __float_as_int(val));
-            }
-        }
-        __syncthreads();
-        if (P.dbg_grid) {
-            float *g = P.dbg_grid + ((size_t)b * D + d) * R * R;
-            for (int i = tid; i < R * R; i += NT) {
-                const float t = sm.G[i];
-                g[i] = t > thr ? t : 0.0f;
-            }
-        }
-
-        {
-            const int glo = max(ylo - 4, 0), ghi = min(yhi + 2, Q - 1);   // smoothed rows of this slice
-            const int ch = max((ghi - glo + NW) / NW, 2);                 // rows per warp, 2..7
-            const int y0 = glo + warp * ch;
-            if (y0 <= ghi) {
-                const int y1 = min(y0 + ch - 1, ghi);
-                float4 h0, h1, h2, h3, h4;                 // horizontal maxima of raw rows r-4 .. r
-                float4 pa, pb, pc;                         // pooled rows q-2, q-1, q
-                float la, lb, lc, ra, rb, rc;              // their left / right neighbour columns
-                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                h0 = h1 = h2 = h3 = h4 = z4;
-                pa = pb = pc = z4;
-                la = lb = lc = ra = rb = rc = 0.0f;
-#pragma unroll
-                for (int i = 0; i < CH + 6; ++i) {
-                    const int r = y0 - 2 + i;              // raw row streamed in this step
-                    if (r > y1 + 4) break;                 // warp-uniform
-                    // H(r, x) = max G(r, x-1 .. x+3) for x in [0, 110); columns 110, 111 are padding
-                    float4 h = z4;
-                    if (r >= ylo && r <= yhi) {            // warp-uniform: other rows hold no point of d
-                        float4 a = z4;
-                        if (lane < R / 4) a = reinterpret_cast<const float4 *>(sm.G + r * R)[lane];
-                        const float left = __shfl_up_sync(0xffffffffu, a.w, 1);
-                        const float rx = __shfl_down_sync(0xffffffffu, a.x, 1);
-                        const float ry = __shfl_down_sync(0xffffffffu, a.y, 1);
-                        const float rz = __shfl_down_sync(0xffffffffu, a.z, 1);
-                        const float l = lane == 0 ? 0.0f : left;
-                        const float m3 = max3f(a.z, a.w, rx);
-                        h.x = max3f(max3f(l, a.x, a.y), a.z, a.w);
-                        h.y = max3f(m3, a.x, a.y);
-                        h.z = max3f(m3, a.y, ry);
-                        h.w = max3f(m3, ry, rz);
-                        if (lane == R / 4 - 1) { h.z = 0.0f; h.w = 0.0f; }
-                    }
-                    h0 = h1; h1 = h2; h2 = h3; h3 = h4; h4 = h;
-                    if (i < 4) continue;
-                    // P(q, x) = max H(q-1 .. q+3, x), q = r - 3; rows 110, 111 are padding; cut the
-                    // leftovers of lower slices
-                    const int q = r - 3;
-                    float4 pl = z4;
-                    if (q >= 0 && q < Q) {
-                        pl.x = max3f(max3f(h0.x, h1.x, h2.x), h3.x, h4.x);
-                        pl.y = max3f(max3f(h0.y, h1.y, h2.y), h3.y, h4.y);
-                        pl.z = max3f(max3f(h0.z, h1.z, h2.z), h3.z, h4.z);
-                        pl.w = max3f(max3f(h0.w, h1.w, h2.w), h3.w, h4.w);
-                        pl.x = pl.x > thr ? pl.x : 0.0f;
-                        pl.y = pl.y > thr ? pl.y : 0.0f;
-                        pl.z = pl.z > thr ? pl.z : 0.0f;
-                        pl.w = pl.w > thr ? pl.w : 0.0f;
-                    }
-                    pa = pb; la = lb; ra = rb;
-                    pb = pc; lb = lc; rb = rc;
-                    pc = pl;
-                    lc = __shfl_up_sync(0xffffffffu, pl.w, 1);
-                    rc = __shfl_down_sync(0xffffffffu, pl.x, 1);
-                    if (lane == 0) lc = 0.0f;
-                    if (i < 6) continue;
-                    // 3x3 Gaussian (zero padding) of pooled rows y-1, y, y+1 (y = r - 4) as a row-major
-                    // FMA chain, then the running max over depth
-                    const int y = r - 4;
-                    const float ta[6] = {la, pa.x, pa.y, pa.z, pa.w, ra};
-                    const float tb[6] = {lb, pb.x, pb.y, pb.z, pb.w, rb};
-                    const float tc[6] = {lc, pc.x, pc.y, pc.z, pc.w, rc};
+            __syncthreads();
+            // Gaussian + depth max over the bounding box: a row of ns strips is split into nseg
+            // segments of `own` strips plus one halo lane on each side (neighbours come by shuffle),
+            // rpw segment-rows share a warp.
+            {
+                const int nseg = (ns + 29) / 30;
+                const int own = (ns + nseg - 1) / nseg;
+                const int lw = own + 2;
+                const int rpw = 32 / lw;
+                const int rg = lane / lw, j = lane - rg * lw;
+                const int tasks = (gy1 - gy0 + 1) * nseg;
+                for (int t0 = warp * rpw; t0 < tasks; t0 += NW * rpw) {
+                    const int t = t0 + rg;
+                    const bool valid = rg < rpw && t < tasks;
+                    const int rrow = nseg == 1 ? t : t >> 1, seg = nseg == 1 ? 0 : t & 1;
+                    const int y = gy0 + rrow;
+                    const int s = gs_lo + seg * own - 1 + j;
+                    const bool inreg = valid && s >= gs_lo && s <= gs_hi;
+                    const bool owner = inreg && j >= 1 && j <= own;
+                    float ta[6], tb[6], tc[6];
+                    auto load = [&](int rr, float (&tt)[6]) {
+                        float4 cc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (inreg && rr >= py0 && rr <= py1)
+                            cc = reinterpret_cast<const float4 *>(sm.G + rr * R)[s];
+                        tt[0] = __shfl_up_sync(0xffffffffu, cc.w, 1);
+                        tt[5] = __shfl_down_sync(0xffffffffu, cc.x, 1);
+                        tt[1] = cc.x; tt[2] = cc.y; tt[3] = cc.z; tt[4] = cc.w;
+                    };
+                    load(y - 1, ta);
+                    load(y, tb);
+                    load(y + 1, tc);
                     float o[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float acc = __fmul_rn(w[0], ta[j]);
-                        acc = __fmaf_rn(w[1], ta[j + 1], acc);
-                        acc = __fmaf_rn(w[2], ta[j + 2], acc);
-                        acc = __fmaf_rn(w[3], tb[j], acc);
-                        acc = __fmaf_rn(w[4], tb[j + 1], acc);
-                        acc = __fmaf_rn(w[5], tb[j + 2], acc);
-                        acc = __fmaf_rn(w[6], tc[j], acc);
-                        acc = __fmaf_rn(w[7], tc[j + 1], acc);
-                        acc = __fmaf_rn(w[8], tc[j + 2], acc);
-                        o[j] = acc;
-                    }
-                    if (lane == R / 4 - 1) { o[2] = 0.0f; o[3] = 0.0f; }
-                    if (lane < R / 4) {
-                        float4 *dst = reinterpret_cast<float4 *>(sm.IMG + y * R) + lane;
-                        *dst = max4(*dst, make_float4(o[0], o[1], o[2], o[3]));
+                    gauss4(w, ta, tb, tc, o);
+                    if (s == NS - 1) { o[2] = 0.0f; o[3] = 0.0f; }      // columns Q, Q+1 are padding
+                    if (owner) {
+                        float *dst = IMG + y * R + 4 * s;
+                        img_st4<ISM>(dst, max4(img_ld4<ISM>(dst), make_float4(o[0], o[1], o[2], o[3])));
                     }
                 }
             }
+            __syncthreads();
+            base += cnt;
         }
-        __syncthreads();
+    } else {
+        // Dense path.  The grid buffer is cleared ONCE.  Slices are visited in increasing depth and a
+        // point of slice d carries a value in (d-1, d], so whatever lower slices left behind is <= d-1:
+        // scatter-max simply overwrites it, and after pooling (max commutes with the monotone cut)
+        // everything <= d-1 is cut to the 0 an empty cell holds.  Only slices whose values can tie with
+        // a lower one (0/1: both 1.0, 7: 6.0 like the top of slice 6 -- both only reachable through
+        // rounding) clear again.  Per slice that leaves two block barriers: scatter | fused stencil
+        // pass.  In the fused pass a warp owns a chunk of smoothed rows of one 28-strip segment and
+        // streams the raw rows it needs through registers: horizontal 5-max (shuffles), vertical 5-max
+        // over a ring of 5 rows, cut, 3x3 Gaussian over a ring of 3 pooled rows, running depth max into
+        // IMG.  Rows outside [ylo, yhi] hold no point of the slice and are not even loaded.
+        bool dirty = false;       // G holds values of a lower slice
+        for (int d = 0; d < D; ++d) {
+            if (!((mask >> d) & 1u)) {
+                if (P.dbg_grid) {
+                    float *g = P.dbg_grid + ((size_t)b * D + d) * R * R;
+                    for (int i = tid; i < R * R; i += NT) g[i] = 0.0f;
+                }
+                continue;
+            }
+            const int ylo = sm.ylo[d], yhi = sm.yhi[d];
+            float thr = 0.0f;
+            if (dirty) {
+                if (d >= 2 && d <= D - 2) {
+                    thr = (float)(d - 1);
+                } else {
+                    for (int i = tid; i < R * R / 4; i += NT)
+                        reinterpret_cast<float4 *>(sm.G)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    __syncthreads();
+                }
+            }
+            dirty = true;
+            {
+                auto put = [&](const uint2 e) {
+                    if ((int)(e.x >> 16) == d)
+                        atomicMax(reinterpret_cast<int *>(sm.G) + (int)((e.x >> 8) & 255u) * R + (int)(e.x & 255u),
+                                  (int)e.y);
+                };
+                const int ncache = min(n, CAP);
+                for (int i = tid; i < ncache; i += NT) put(sm.cache[i]);
+                // pooled points: 4 independent L2 loads in flight per thread
+                for (int i0 = tid; i0 < npool; i0 += 4 * NT) {
+                    uint2 e[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        e[k] = i0 + k * NT < npool ? __ldcg(pool + i0 + k * NT) : make_uint2(0xffffffffu, 0u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) put(e[k]);
+                }
+                // beyond the pool (N > CAP + POOL), or every pool of this SM taken (cannot happen at
+                // two resident CTAs per SM): rotate and quantise again
+                for (int i = CAP + npool + tid; i < n; i += NT) {
+                    float qx, qy, qz, val; int X, Y, zi;
+                    rotate_point(pts + 3 * i, rm, fused, qx, qy, qz);
+                    quantise<R>(qx, qy, qz, qn, P, X, Y, zi, val);
+                    if (zi == d) atomicMax(reinterpret_cast<int *>(sm.G) + Y * R + X, __float_as_int(val));
+                }
+            }
+            __syncthreads();
+            if (P.dbg_grid) {
+                float *g = P.dbg_grid + ((size_t)b * D + d) * R * R;
+                for (int i = tid; i < R * R; i += NT) {
+                    const float t = sm.G[i];
+                    g[i] = t > thr ? t : 0.0f;
+                }
+            }
+            {
+                constexpr int NSEG = GE::NSEG;
+                const int glo = max(ylo - 4, 0), ghi = min(yhi + 2, Q - 1);   // smoothed rows of this slice
+                const int rows = ghi - glo + 1;
+                const int ch = min(max((rows * NSEG + NW - 1) / NW, 2), CH);  // rows per task, 2..7
+                const int nchunks = (rows + ch - 1) / ch;
+                for (int task = warp; task < nchunks * NSEG; task += NW) {
+                    const int chunk = task / NSEG, seg = task - chunk * NSEG;
+                    const int y0 = glo + chunk * ch;
+                    const int y1 = min(y0 + ch - 1, ghi);
+                    // segment 0: strips 0..31, lanes 0..27 own; segment 1 (R = 224): strips 24..55,
+                    // lanes 4..31 own (the other lanes only feed their neighbours)
+                    const int strip = seg * 24 + lane;
+                    const bool owner = strip < NS && (seg == 0 ? lane < 28 : lane >= 4);
+                    float4 h0, h1, h2, h3, h4;                 // horizontal maxima of raw rows r-4 .. r
+                    float4 pa, pb, pc;                         // pooled rows q-2, q-1, q
+                    float la, lb, lc, ra, rb, rc;              // their left / right neighbour columns
+                    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    h0 = h1 = h2 = h3 = h4 = z4;
+                    pa = pb = pc = z4;
+                    la = lb = lc = ra = rb = rc = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < CH + 6; ++i) {
+                        const int r = y0 - 2 + i;              // raw row streamed in this step
+                        if (r > y1 + 4) break;                 // warp-uniform
+                        // H(r, x) = max G(r, x-1 .. x+3) for x in [0, Q); columns Q, Q+1 are padding
+                        float4 h = z4;
+                        if (r >= ylo && r <= yhi) {            // warp-uniform: other rows hold no point of d
+                            float4 a = z4;
+                            if (strip < NS) a = reinterpret_cast<const float4 *>(sm.G + r * R)[strip];
+                            const float left = __shfl_up_sync(0xffffffffu, a.w, 1);
+                            const float rx = __shfl_down_sync(0xffffffffu, a.x, 1);
+                            const float ry = __shfl_down_sync(0xffffffffu, a.y, 1);
+                            const float rz = __shfl_down_sync(0xffffffffu, a.z, 1);
+                            const float l = strip == 0 ? 0.0f : left;
+                            const float m3 = max3f(a.z, a.w, rx);
+                            h.x = max3f(max3f(l, a.x, a.y), a.z, a.w);
+                            h.y = max3f(m3, a.x, a.y);
+                            h.z = max3f(m3, a.y, ry);
+                            h.w = max3f(m3, ry, rz);
+                            if (strip == NS - 1) { h.z = 0.0f; h.w = 0.0f; }
+                        }
+                        h0 = h1; h1 = h2; h2 = h3; h3 = h4; h4 = h;
+                        if (i < 4) continue;
+                        // P(q, x) = max H(q-1 .. q+3, x), q = r - 3; rows Q, Q+1 are padding; cut the
+                        // leftovers of lower slices
+                        const int q = r - 3;
+                        float4 pl = z4;
+                        if (q >= 0 && q < Q) {
+                            pl.x = max3f(max3f(h0.x, h1.x, h2.x), h3.x, h4.x);
+                            pl.y = max3f(max3f(h0.y, h1.y, h2.y), h3.y, h4.y);
+                            pl.z = max3f(max3f(h0.z, h1.z, h2.z), h3.z, h4.z);
+                            pl.w = max3f(max3f(h0.w, h1.w, h2.w), h3.w, h4.w);
+                            pl.x = pl.x > thr ? pl.x : 0.0f;
+                            pl.y = pl.y > thr ? pl.y : 0.0f;
+                            pl.z = pl.z > thr ? pl.z : 0.0f;
+                            pl.w = pl.w > thr ? pl.w : 0.0f;
+                        }
+                        pa = pb; la = lb; ra = rb;
+                        pb = pc; lb = lc; rb = rc;
+                        pc = pl;
+                        lc = __shfl_up_sync(0xffffffffu, pl.w, 1);
+                        rc = __shfl_down_sync(0xffffffffu, pl.x, 1);
+                        if (strip == 0) lc = 0.0f;
+                        if (i < 6) continue;
+                        // 3x3 Gaussian (zero padding) of pooled rows y-1, y, y+1 (y = r - 4), then the
+                        // running max over depth
+                        const int y = r - 4;
+                        const float ta[6] = {la, pa.x, pa.y, pa.z, pa.w, ra};
+                        const float tb[6] = {lb, pb.x, pb.y, pb.z, pb.w, rb};
+                        const float tc[6] = {lc, pc.x, pc.y, pc.z, pc.w, rc};
+                        float o[4];
+                        gauss4(w, ta, tb, tc, o);
+                        if (strip == NS - 1) { o[2] = 0.0f; o[3] = 0.0f; }
+                        if (owner) {
+                            float *dst = IMG + y * R + 4 * strip;
+                            img_st4<ISM>(dst, max4(img_ld4<ISM>(dst), make_float4(o[0], o[1], o[2], o[3])));
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
     }
 
     if (big) {   // hand the pool back (every read of it is behind the last slice's barriers)
-        __syncthreads();
         if (tid == 0 && sm.spill_slot >= 0) {
             __threadfence();
             atomicExch(&P.spill_flags[sm.spill_slot], 0);
         }
     }
 
-    // ---- phase 4: img / max(img), 1 - x  (rows the emit reads; everything else is background) ----
+    // ---- phase 4: img / max(img), 1 - x  (cells the emit reads; everything else is background) ----
     {
+        const int us_lo = vlo >> 2, us_hi = vhi >> 2;
         float m = 0.0f;
-        for (int i = tid; i < (uhi - ulo + 1) * (R / 4); i += NT) {
-            const float4 t = reinterpret_cast<const float4 *>(sm.IMG + ulo * R)[i];
-            m = fmaxf(fmaxf(m, fmaxf(t.x, t.y)), fmaxf(t.z, t.w));
-        }
+        for (int r = ulo + warp; r <= uhi; r += NW)
+            for (int s = us_lo + lane; s <= us_hi; s += 32) {
+                const float4 t = img_ld4<ISM>(IMG + r * R + 4 * s);
+                m = fmaxf(fmaxf(m, fmaxf(t.x, t.y)), fmaxf(t.z, t.w));
+            }
         m = warp_max(m);
         if (lane == 0) sm.red[warp] = m;
         __syncthreads();
@@ -573,158 +806,146 @@ __global__ void __launch_bounds__(NT, 2) projection_kernel(const ProjParams P)
         __syncthreads();
         const float mx = sm.mx;
         const float rc_mx = __frcp_rn(mx);
-        for (int i = tid; i < (nhi - nlo + 1) * (R / 4); i += NT) {
-            float4 t = reinterpret_cast<float4 *>(sm.IMG + nlo * R)[i];
-            t.x = __fsub_rn(1.0f, div_rn(t.x, mx, rc_mx, false));
-            t.y = __fsub_rn(1.0f, div_rn(t.y, mx, rc_mx, false));
-            t.z = __fsub_rn(1.0f, div_rn(t.z, mx, rc_mx, false));
-            t.w = __fsub_rn(1.0f, div_rn(t.w, mx, rc_mx, false));
-            reinterpret_cast<float4 *>(sm.IMG + nlo * R)[i] = t;
-        }
+        for (int r = nlo + warp; r <= nhi; r += NW)
+            for (int s = ns_lo + lane; s <= ns_hi; s += 32) {
+                float4 t = img_ld4<ISM>(IMG + r * R + 4 * s);
+                t.x = __fsub_rn(1.0f, div_rn(t.x, mx, rc_mx, false));
+                t.y = __fsub_rn(1.0f, div_rn(t.y, mx, rc_mx, false));
+                t.z = __fsub_rn(1.0f, div_rn(t.z, mx, rc_mx, false));
+                t.w = __fsub_rn(1.0f, div_rn(t.w, mx, rc_mx, false));
+                img_st4<ISM>(IMG + r * R + 4 * s, t);
+            }
         __syncthreads();
         if (P.dbg_dens) {
             float *dd = P.dbg_dens + (size_t)b * Q * Q;
             for (int i = tid; i < Q * Q; i += NT) {
-                const int y = i / Q;
-                dd[i] = (y >= nlo && y <= nhi) ? sm.IMG[y * R + (i - y * Q)] : 1.0f;
+                const int y = i / Q, x = i - y * Q;
+                const bool in = y >= nlo && y <= nhi && (x >> 2) >= ns_lo && (x >> 2) <= ns_hi;
+                dd[i] = in ? img_ld<ISM>(IMG + y * R + x) : 1.0f;
             }
         }
     }
 
-    // ---- phase 5: bilinear 110 -> 224 (align_corners), floor(x*255), patch-major bf16 tiles ------
-    // Two halves: HI[y][ox] = fma(IMG[y][x0], lw0, IMG[y][x1]*lw1) for 56 source rows at a time
-    // (held in the grid buffer), then out = fma(HI[y0], lh0, HI[y1]*lh1) -- the exact contraction
-    // pattern of torch-CPU's separable interpolation on an FMA host.  One warp per output row; rows
-    // whose two source rows lie outside [ulo, uhi] are copied from the precomputed background tile.
-    op_t *tile = P.tiles ? P.tiles + (size_t)b * VG_TILE_ELEMS : nullptr;
-    uint8_t *u8 = P.u8 ? P.u8 + (size_t)b * S * S : nullptr;
-    const ProjTables *__restrict__ tab = P.tab;
-    int cx0 = 0, cx1 = 0;
-    float clw0 = 0.f, clw1 = 0.f;
-    if (tid < 2 * S) {
-        const int ox = tid % S;
-        cx0 = __ldg(&tab->i0[ox]);
-        clw0 = __ldg(&tab->l0[ox]);
-        clw1 = __ldg(&tab->l1[ox]);
-        cx1 = cx0 + (cx0 < Q - 1 ? 1 : 0);
-    }
-    const f32x2 k255 = pack2(255.0f, 255.0f), kmagic = pack2(8388608.0f, 8388608.0f);
-    for (int half = 0; half < 2; ++half) {
-        const int ybase = half == 0 ? 0 : Q - HI_ROWS + 1;        // source rows 0..55 / 55..109
-        const int nrows = half == 0 ? HI_ROWS : Q - ybase;        // 56 / 55
-        const int oy_beg = half == 0 ? 0 : 113, oy_end = half == 0 ? 113 : S;
-        if (tid < 2 * S) {
-            const int ox = tid % S;
-            const int r_lo = max(nlo, ybase), r_hi = min(nhi, ybase + nrows - 1);
-            for (int y = r_lo + tid / S; y <= r_hi; y += 2) {
-                const float *row = sm.IMG + y * R;
-                sm.G[(y - ybase) * S + ox] = __fmaf_rn(row[cx0], clw0, __fmul_rn(row[cx1], clw1));
-            }
+    // ---- phase 5: bilinear Q -> 224 (align_corners), floor(x*255), patch-major tiles ---------------
+    // HI[y][ox] = fma(IMG[y][x0], lw0, IMG[y][x1]*lw1) for up to HI_ROWS source rows at a time (held
+    // in the grid buffer), then out = fma(HI[y0], lh0, HI[y1]*lh1) -- the exact contraction pattern of
+    // torch-CPU's separable interpolation on an FMA host.  Only the active rows x column groups are
+    // computed (the rest was copied from the background tile above); threads map to a fixed output
+    // column (horizontal pass) / column group (vertical pass) and stride over the rows.
+    if (oy_hi < oy_lo || g_hi < g_lo) return;          // cannot happen for a non-degenerate cluster
+    {
+        constexpr int HI_ROWS = GE::HI_ROWS;
+        const int ng = g_hi - g_lo + 1, ncols = 8 * ng;
+        const int h_nrl = NT / ncols, h_rl = tid / ncols;       // horizontal pass: row lanes
+        const int ox = 8 * g_lo + (tid - h_rl * ncols);
+        int cx0 = 0, cx1 = 0;
+        float clw0 = 0.f, clw1 = 0.f;
+        if (h_rl < h_nrl) {
+            cx0 = __ldg(&tab->i0[ox]);
+            clw0 = __ldg(&tab->l0[ox]);
+            clw1 = __ldg(&tab->l1[ox]);
+            cx1 = cx0 + (cx0 < Q - 1 ? 1 : 0);
         }
-        __syncthreads();
-        // pure background rows first: their loads are independent, so they all go out before the
-        // first store instead of paying one L2 round trip per row
-#pragma unroll
-        for (int k0 = 0; k0 < 8; k0 += 4) {        // up to 8 rows per warp and half, 4 in flight
-            uint4 bt[4];
-            uint2 bu[4];
-            bool bg[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int oy = oy_beg + warp + (k0 + k) * NW;
-                bg[k] = false;
-                if (oy < oy_end && lane < S / 8) {
-                    int y0; float t0, t1;
-                    lin_idx(oy, y0, t0, t1);
+        const int v_nrl = NT / ng, v_rl = tid / ng;             // vertical pass: row lanes
+        const int g = g_lo + (tid - v_rl * ng);
+        const f32x2 k255 = pack2(255.0f, 255.0f), kmagic = pack2(8388608.0f, 8388608.0f);
+        const float scale = __fdiv_rn((float)(Q - 1), (float)(S - 1));
+        int oy_cur = oy_lo;
+        while (oy_cur <= oy_hi) {
+            int ybase; float t0, t1;
+            lin_idx(Q, oy_cur, ybase, t0, t1);
+            const int ylast = min(ybase + HI_ROWS - 1, nhi);
+            int oy_end = oy_hi;
+            if (ylast < nhi) {
+                // last output row whose two source rows are both inside [ybase, ylast]
+                int gss = min(max((int)((float)ylast / scale), oy_cur), oy_hi);
+                auto y1_of = [&](int oy) { int a; float u0, u1; lin_idx(Q, oy, a, u0, u1); return a + (a < Q - 1 ? 1 : 0); };
+                while (gss + 1 <= oy_hi && y1_of(gss + 1) <= ylast) ++gss;
+                while (gss > oy_cur && y1_of(gss) > ylast) --gss;
+                oy_end = gss;
+            }
+            if (h_rl < h_nrl)
+                for (int y = ybase + h_rl; y <= ylast; y += h_nrl) {
+                    const float *row = IMG + y * R;
+                    sm.G[(y - ybase) * S + ox] =
+                        __fmaf_rn(img_ld<ISM>(row + cx0), clw0, __fmul_rn(img_ld<ISM>(row + cx1), clw1));
+                }
+            __syncthreads();
+            if (v_rl < v_nrl)
+                for (int oy = oy_cur + v_rl; oy <= oy_end; oy += v_nrl) {
+                    int y0; float lh0, lh1;
+                    lin_idx(Q, oy, y0, lh0, lh1);     // same arithmetic as the column table (bit-identical)
                     const int y1 = y0 + (y0 < Q - 1 ? 1 : 0);
-                    bg[k] = y1 < ulo || y0 > uhi;
-                    if (bg[k]) {
-                        const int patch = (oy >> 4) * 14 + (lane >> 1);
-                        const int inner = (oy & 15) * 16 + (lane & 1) * 8;
-                        if (tile) bt[k] = __ldg(&tab->bg_tile[(patch * 256 + inner) >> 3]);
-                        if (u8) bu[k] = __ldg(&tab->bg_u8[(oy * S + 8 * lane) >> 3]);
+                    const int patch = (oy >> 4) * 14 + (g >> 1);
+                    const int inner = (oy & 15) * 16 + (g & 1) * 8;
+                    const f32x2 h0 = pack2(lh0, lh0), h1 = pack2(lh1, lh1);
+                    const ulonglong2 *r0 = reinterpret_cast<const ulonglong2 *>(sm.G + (y0 - ybase) * S + 8 * g);
+                    const ulonglong2 *r1 = reinterpret_cast<const ulonglong2 *>(sm.G + (y1 - ybase) * S + 8 * g);
+                    const ulonglong2 a0 = r0[0], a1 = r0[1], b0 = r1[0], b1 = r1[1];
+                    const f32x2 ta[4] = {a0.x, a0.y, a1.x, a1.y};
+                    const f32x2 tb[4] = {b0.x, b0.y, b1.x, b1.y};
+                    unsigned fb[8];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const f32x2 o = fma2(ta[j], h0, mul2(tb[j], h1));
+                        const f32x2 q = sub2(add2_rz(mul2(o, k255), kmagic), kmagic);
+                        float q0, q1;
+                        unpack2(q, q0, q1);
+                        fb[2 * j] = __float_as_uint(q0);
+                        fb[2 * j + 1] = __float_as_uint(q1);
+                    }
+                    if (tile) {
+                        uint4 pk;
+#ifndef VG_OPERAND_BF16
+                        pk.x = pack_op(__uint_as_float(fb[0]), __uint_as_float(fb[1]));
+                        pk.y = pack_op(__uint_as_float(fb[2]), __uint_as_float(fb[3]));
+                        pk.z = pack_op(__uint_as_float(fb[4]), __uint_as_float(fb[5]));
+                        pk.w = pack_op(__uint_as_float(fb[6]), __uint_as_float(fb[7]));
+#else
+                        // integers 0..255 are exact in bf16: the bf16 pattern is the high half of the fp32
+                        pk.x = __byte_perm(fb[0], fb[1], 0x7632);
+                        pk.y = __byte_perm(fb[2], fb[3], 0x7632);
+                        pk.z = __byte_perm(fb[4], fb[5], 0x7632);
+                        pk.w = __byte_perm(fb[6], fb[7], 0x7632);
+#endif
+                        *reinterpret_cast<uint4 *>(tile + patch * 256 + inner) = pk;
+                    }
+                    if (u8) {
+                        unsigned lo = 0, hi = 0;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            lo |= ((unsigned)__uint_as_float(fb[j])) << (8 * j);
+                            hi |= ((unsigned)__uint_as_float(fb[4 + j])) << (8 * j);
+                        }
+                        *reinterpret_cast<uint2 *>(u8 + oy * S + 8 * g) = make_uint2(lo, hi);
                     }
                 }
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int oy = oy_beg + warp + (k0 + k) * NW;
-                if (bg[k]) {
-                    const int patch = (oy >> 4) * 14 + (lane >> 1);
-                    const int inner = (oy & 15) * 16 + (lane & 1) * 8;
-                    if (tile) *reinterpret_cast<uint4 *>(tile + patch * 256 + inner) = bt[k];
-                    if (u8) *reinterpret_cast<uint2 *>(u8 + oy * S + 8 * lane) = bu[k];
-                }
-            }
+            oy_cur = oy_end + 1;
+            if (oy_cur <= oy_hi) __syncthreads();      // the next pass overwrites the HI rows
         }
-        for (int oy = oy_beg + warp; oy < oy_end; oy += NW) {
-            int y0; float lh0, lh1;
-            lin_idx(oy, y0, lh0, lh1);     // same arithmetic as the column table (bit-identical)
-            const int y1 = y0 + (y0 < Q - 1 ? 1 : 0);
-            if (lane >= S / 8) continue;
-            const int g = lane;
-            const int patch = (oy >> 4) * 14 + (g >> 1);
-            const int inner = (oy & 15) * 16 + (g & 1) * 8;
-            if (y1 < ulo || y0 > uhi) continue;    // warp-uniform: pure background row, done above
-            const f32x2 h0 = pack2(lh0, lh0), h1 = pack2(lh1, lh1);
-            const ulonglong2 *r0 = reinterpret_cast<const ulonglong2 *>(sm.G + (y0 - ybase) * S + 8 * g);
-            const ulonglong2 *r1 = reinterpret_cast<const ulonglong2 *>(sm.G + (y1 - ybase) * S + 8 * g);
-            const ulonglong2 a0 = r0[0], a1 = r0[1], b0 = r1[0], b1 = r1[1];
-            const f32x2 ta[4] = {a0.x, a0.y, a1.x, a1.y};
-            const f32x2 tb[4] = {b0.x, b0.y, b1.x, b1.y};
-            unsigned fb[8];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const f32x2 o = fma2(ta[j], h0, mul2(tb[j], h1));
-                const f32x2 q = sub2(add2_rz(mul2(o, k255), kmagic), kmagic);
-                float q0, q1;
-                unpack2(q, q0, q1);
-                fb[2 * j] = __float_as_uint(q0);
-                fb[2 * j + 1] = __float_as_uint(q1);
-            }
-            if (tile) {
-                uint4 pk;
-#ifdef VG_OPERAND_F16
-                pk.x = pack_op(__uint_as_float(fb[0]), __uint_as_float(fb[1]));
-                pk.y = pack_op(__uint_as_float(fb[2]), __uint_as_float(fb[3]));
-                pk.z = pack_op(__uint_as_float(fb[4]), __uint_as_float(fb[5]));
-                pk.w = pack_op(__uint_as_float(fb[6]), __uint_as_float(fb[7]));
-#else
-                // integers 0..255 are exact in bf16: the bf16 pattern is the high half of the fp32
-                pk.x = __byte_perm(fb[0], fb[1], 0x7632);
-                pk.y = __byte_perm(fb[2], fb[3], 0x7632);
-                pk.z = __byte_perm(fb[4], fb[5], 0x7632);
-                pk.w = __byte_perm(fb[6], fb[7], 0x7632);
-#endif
-                *reinterpret_cast<uint4 *>(tile + patch * 256 + inner) = pk;
-            }
-            if (u8) {
-                unsigned lo = 0, hi = 0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    lo |= ((unsigned)__uint_as_float(fb[j])) << (8 * j);
-                    hi |= ((unsigned)__uint_as_float(fb[4 + j])) << (8 * j);
-                }
-                *reinterpret_cast<uint2 *>(u8 + oy * S + 8 * g) = make_uint2(lo, hi);
-            }
-        }
-        __syncthreads();
     }
+}
+
+template <int R>
+int launch_projection_t(VgHandle *h, const ProjParams &P, long long blocks, cudaStream_t st)
+{
+    int rc = vg_set_smem_once(h, reinterpret_cast<const void *>(projection_kernel<R>), sizeof(Smem<R>));
+    if (rc) return rc;
+    projection_kernel<R><<<(unsigned)blocks, NT, sizeof(Smem<R>), st>>>(P);
+    return VG_OK;
 }
 
 }  // namespace
 
 int projection_init(VgHandle *h)
 {
+    const int R = h->cfg.resolution, Q = R - 2;
     ProjTables *t = nullptr;
     VG_CUDA_CHECK(h, cudaMalloc(&t, sizeof(ProjTables)));
-    projection_tables_kernel<<<64, 256>>>(t);
+    h->proj_tables = t;
+    projection_tables_kernel<<<64, 256>>>(t, Q);
     VG_CUDA_CHECK(h, cudaGetLastError());
     VG_CUDA_CHECK(h, cudaDeviceSynchronize());
-    VG_CUDA_CHECK(h, cudaFuncSetAttribute(projection_kernel,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)sizeof(Smem)));
-    h->proj_tables = t;
     // point pools for clusters above CAP points: one per CTA that can be resident (~150 MB)
     int nsmid = 0;
     VG_CUDA_CHECK(h, cudaMemcpy(&nsmid, &t->nsmid, sizeof(int), cudaMemcpyDeviceToHost));
@@ -734,17 +955,19 @@ int projection_init(VgHandle *h)
     VG_CUDA_CHECK(h, cudaMalloc(&h->proj_spill, slots * POOL * sizeof(uint2)));
     VG_CUDA_CHECK(h, cudaMalloc(&h->proj_spill_flags, slots * sizeof(int)));
     VG_CUDA_CHECK(h, cudaMemset(h->proj_spill_flags, 0, slots * sizeof(int)));
+    if (R == 224)    // running depth-max image of the one CTA resident on each SM (~29 MB)
+        VG_CUDA_CHECK(h, cudaMalloc(&h->proj_img_scratch, (size_t)nsmid * Q * R * sizeof(float)));
     VG_CUDA_CHECK(h, cudaDeviceSynchronize());
     return VG_OK;
 }
 
 int launch_projection(VgHandle *h, const float *d_points, const int32_t *d_offsets, int32_t C,
-                      op_t *d_tiles, uint8_t *d_u8, int32_t *d_status,
+                      op_t *d_tiles, uint8_t *d_u8, bool u8_first_only, int32_t *d_status,
                       const VgProjectDebug *dbg, cudaStream_t st)
 {
     const VgConfig &cfg = h->cfg;
-    if (cfg.resolution != R || cfg.depth != D || cfg.image_size != S) {
-        VG_SET_ERR(h, "projection kernel is specialised for R=112, D=8, S=224 (got %d, %d, %d)",
+    if ((cfg.resolution != 112 && cfg.resolution != 224) || cfg.depth != D || cfg.image_size != S) {
+        VG_SET_ERR(h, "projection kernel is specialised for R in {112, 224}, D=8, S=224 (got %d, %d, %d)",
                    cfg.resolution, cfg.depth, cfg.image_size);
         return VG_ESHAPE;
     }
@@ -755,6 +978,7 @@ int launch_projection(VgHandle *h, const float *d_points, const int32_t *d_offse
     P.tab = static_cast<const ProjTables *>(h->proj_tables);
     P.spill = static_cast<uint2 *>(h->proj_spill);
     P.spill_flags = static_cast<int *>(h->proj_spill_flags);
+    P.img_scratch = static_cast<float *>(h->proj_img_scratch);
     P.spill_sms = h->proj_spill_sms;
     P.C = C;
     P.V = cfg.num_views;
@@ -764,15 +988,19 @@ int launch_projection(VgHandle *h, const float *d_points, const int32_t *d_offse
     P.depth_bias = (float)cfg.depth_bias;
     P.one_plus_bias = (float)(1.0 + cfg.depth_bias);
     P.rotate_mode = cfg.rotate_mode;
+    P.div_mode = cfg.div_mode;
     P.tiles = d_tiles;
     P.u8 = d_u8;
+    P.u8_first_only = u8_first_only ? 1 : 0;
     P.status = d_status;
     P.dbg_grid = dbg ? dbg->d_grid : nullptr;
     P.dbg_dens = dbg ? dbg->d_densified : nullptr;
     const long long blocks = (long long)C * cfg.num_views;
     // algorithmic bytes recorded here: the emitted tiles; the caller adds 12 * sum(N) for the points
     VgProfScope prof(h, VG_K_PROJECTION, (double)blocks * VG_TILE_ELEMS * 2.0, st);
-    projection_kernel<<<(unsigned)blocks, NT, sizeof(Smem), st>>>(P);
+    int rc = cfg.resolution == 112 ? launch_projection_t<112>(h, P, blocks, st)
+                                   : launch_projection_t<224>(h, P, blocks, st);
+    if (rc) return rc;
     VG_LAUNCH_CHECK(h);
     return VG_OK;
 }

@@ -59,7 +59,8 @@ class Engine:
     def __init__(self, num_views: int = 4, rot_mat=None, resolution: int = 112, depth: int = 8,
                  image_size: int = 224, obj_ratio: float = 0.8, depth_bias: float = 0.2,
                  gauss=None, logit_scale: float = 100.0, rotate_mode: int = _lib.VG_ROTATE_TORCH_CPU,
-                 device=None, operand_dtype: str = "bf16"):
+                 device=None, operand_dtype: str = "f16", div_mode: int = _lib.VG_DIV_TRUE,
+                 pool_kernel: int = 5, pool_pad: int = 1):
         if not torch.cuda.is_available():
             raise RuntimeError("vilgod_b200 needs an sm_100 CUDA device; there is no CPU fallback")
         self.lib = _lib.load(operand_dtype)
@@ -76,6 +77,7 @@ class Engine:
         cfg.abi_version = _lib.VG_ABI_VERSION
         cfg.resolution, cfg.depth, cfg.image_size = resolution, depth, image_size
         cfg.num_views, cfg.rotate_mode = num_views, rotate_mode
+        cfg.div_mode, cfg.pool_kernel, cfg.pool_pad = div_mode, pool_kernel, pool_pad
         cfg.obj_ratio, cfg.depth_bias, cfg.logit_scale = obj_ratio, depth_bias, logit_scale
         flat = rot.reshape(num_views, 9).numpy()
         for v in range(num_views):
@@ -95,7 +97,8 @@ class Engine:
         with torch.cuda.device(self.device):
             rc = self.lib.vg_create(C.byref(cfg), C.byref(self._h))
         if rc != _lib.VG_OK:
-            raise VilgodError(rc, "vg_create failed (needs an sm_100 device, R=112, D=8, S=224)")
+            raise VilgodError(rc, "vg_create failed (needs an sm_100 device, R in {112, 224}, D=8, "
+                                  "S=224, max-pool 5/1)")
 
     # ------------------------------------------------------------------------------------------
     def close(self):
@@ -178,6 +181,11 @@ class Engine:
         o = torch.as_tensor(offsets).to(device=self.device, dtype=torch.int32).contiguous()
         if p.ndim != 2 or p.shape[1] != 3 or o.ndim != 1 or o.numel() < 1:
             raise ValueError("points must be [sum N, 3] and offsets [C+1]")
+        host = offsets if isinstance(offsets, np.ndarray) else (
+            offsets.numpy() if isinstance(offsets, torch.Tensor) and offsets.device.type == "cpu" else None)
+        if host is not None and host.size:      # cheap when the offsets are on the host anyway
+            if host[0] < 0 or host[-1] > p.shape[0] or np.any(np.diff(host) < 0):
+                raise ValueError("offsets must be non-decreasing within [0, len(points)]")
         return p, o, o.numel() - 1
 
     def canonicalise(self, points_raw, offsets, transform_to_ego=None):
@@ -252,25 +260,40 @@ class Engine:
                                          Cn, _ptr(vc), _ptr(vs), _stream()))
         return vc, vs
 
-    def classify(self, points, offsets, want_feats=True, out=None):
+    def classify(self, points, offsets, want_feats=True, out=None, want_depth_u8=False):
         """The fused surface: device (or host) packed clusters -> device results.
         Returns dict(probs [C,V,P], top1 [C,V], feats [C,V,512], voted_class [C], voted_score [C],
-        status [C])."""
+        status [C]) and, with ``want_depth_u8``, depth_u8 [C,224,224]: the first view's image of
+        every cluster (what the reference keeps as ``det.depth_image``).
+        Under CUDA-graph capture keep ``out`` and the workspace alive (and call ``workspace()`` with
+        the largest batch first): a later, larger batch reallocates the workspace and a graph that
+        captured the old one must not be replayed."""
         p, o, Cn = self._packed(points, offsets)
         V, P = self.num_views, self.num_prompts
         ws = self.workspace(Cn * V)
         if out is None:
-            out = self.alloc_outputs(Cn, want_feats)
+            out = self.alloc_outputs(Cn, want_feats, want_depth_u8)
+        else:
+            for k, shape in (("probs", (Cn, V, P)), ("top1", (Cn, V)), ("voted_class", (Cn,)),
+                             ("voted_score", (Cn,)), ("status", (Cn,)), ("feats", (Cn, V, 512)),
+                             ("depth_u8", (Cn, self.image_size, self.image_size))):
+                t = out.get(k)
+                if t is None and k in ("feats", "depth_u8"):
+                    continue
+                if t is None or tuple(t.shape) != shape or not t.is_contiguous() or t.device != self.device:
+                    raise ValueError(f"out[{k!r}] must be a contiguous {shape} tensor on {self.device}")
         with torch.cuda.device(self.device):
             self._check(self.lib.vg_classify(
                 self._h, _ptr(p), _ptr(o), Cn, _ptr(out["probs"]), _ptr(out["top1"]),
                 _ptr(out.get("feats")), _ptr(out["voted_class"]), _ptr(out["voted_score"]),
-                _ptr(out["status"]), _ptr(ws), ws.numel(), _stream()))
+                _ptr(out["status"]), _ptr(out.get("depth_u8")), _ptr(ws), ws.numel(), _stream()))
         return out
 
-    def alloc_outputs(self, Cn, want_feats=True):
+    def alloc_outputs(self, Cn, want_feats=True, want_depth_u8=False):
         V, P, d = self.num_views, self.num_prompts, self.device
         return dict(
+            depth_u8=torch.empty((Cn, self.image_size, self.image_size), dtype=torch.uint8, device=d)
+            if want_depth_u8 else None,
             probs=torch.empty((Cn, V, P), dtype=torch.float32, device=d),
             top1=torch.empty((Cn, V), dtype=torch.int32, device=d),
             feats=torch.empty((Cn, V, 512), dtype=torch.float32, device=d) if want_feats else None,
@@ -300,6 +323,28 @@ class Engine:
                                               epilogue, _ptr(out), _stream()))
         return out
 
+    def test_gemm_lnf(self, a, w, bias, epilogue, stats, colsum=None, x_inout=None):
+        """The LayerNorm-folded GEMM instantiations of the tower.  bf16-output epilogues: returns out
+        [M,N]; residual epilogue: ``x_inout`` fp32 [M,768] is updated in place, returns
+        (x, xb [M,768] operand-typed copy) and fills ``stats`` [M,3,2]."""
+        M, K = a.shape
+        N = w.shape[0]
+        resid = epilogue == _lib.VG_EPI_BIAS_RESID_F32
+        out = x_inout if resid else torch.empty((M, N), device=self.device, dtype=self.op_torch_dtype)
+        xb = torch.empty((M, N), device=self.device, dtype=self.op_torch_dtype) if resid else None
+        with torch.cuda.device(self.device):
+            self._check(self.lib.vg_test_gemm_lnf(self._h, _ptr(a), _ptr(w), _ptr(bias), _ptr(colsum),
+                                                  _ptr(stats), _ptr(xb), M, N, K, epilogue, _ptr(out),
+                                                  _stream()))
+        return (out, xb) if resid else out
+
+    def test_gemm_patch(self, tiles, w, table, x):
+        """Patch embedding on the production kernel: rows 1..196 of x [B,197,768] fp32 are written."""
+        with torch.cuda.device(self.device):
+            self._check(self.lib.vg_test_gemm_patch(self._h, _ptr(tiles), _ptr(w), _ptr(table),
+                                                    tiles.shape[0], _ptr(x), _stream()))
+        return x
+
     def test_attention(self, qkv):
         B = qkv.shape[0]
         out = torch.empty((B, 197, 768), dtype=self.op_torch_dtype, device=self.device)
@@ -315,7 +360,7 @@ class Engine:
         return y
 
 
-def u8_to_tiles(u8: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
+def u8_to_tiles(u8: torch.Tensor, dtype=torch.float16) -> torch.Tensor:
     """uint8 [B,224,224] -> patch-major tiles [B,196,256] in the engine's operand dtype (layout
     plumbing for callers that already hold images, e.g. ClipWrapper.predict_clip_labels)."""
     B = u8.shape[0]
