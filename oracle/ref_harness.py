@@ -33,7 +33,18 @@ import sys
 import types
 import warnings
 
-REFERENCE_ROOT = os.environ.get("VILGOD_REFERENCE_ROOT", "/root/reference")
+def _find_reference_root():
+    """The mounted tree in the build container, else the byte-for-byte copy oracle/make_ref.py stages
+    under oracle/_ref (git-ignored; travels to the GPU box for bench.py's reference arm)."""
+    cands = [os.environ.get("VILGOD_REFERENCE_ROOT"), "/root/reference",
+             os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "src", "utils", "mv_utils.py")):
+            return c
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 _STUB_TOPLEVEL = (
     "pcdet", "pytorch3d", "pyransac3d", "kornia", "hdbscan", "easydict", "filterpy",
@@ -114,6 +125,24 @@ def _instantiate(cfg, *args, **kwargs):
 _installed = False
 
 
+_cuda_originals = None
+
+
+def force_cpu(on=True):
+    """bench.py's CPU legs run on a box that HAS a GPU: make the reference's unconditional .cuda()
+    calls (src/utils/mv_utils.py:165-171, zero_shot_detector.py:394,405) no-ops for their duration,
+    and restore torch afterwards."""
+    global _cuda_originals
+    import torch
+    if on and _cuda_originals is None:
+        _cuda_originals = (torch.Tensor.cuda, torch.nn.Module.cuda)
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        torch.nn.Module.cuda = lambda self, *a, **k: self
+    elif not on and _cuda_originals is not None:
+        torch.Tensor.cuda, torch.nn.Module.cuda = _cuda_originals
+        _cuda_originals = None
+
+
 def install_shims():
     """Idempotent.  Must run before any reference module is imported."""
     global _installed
@@ -152,8 +181,7 @@ def install_shims():
     sys.meta_path.append(_StubFinder())
 
     if not torch.cuda.is_available():
-        torch.Tensor.cuda = lambda self, *a, **k: self
-        torch.nn.Module.cuda = lambda self, *a, **k: self
+        force_cpu(True)
 
     for p in (REFERENCE_ROOT, os.path.join(REFERENCE_ROOT, "third_party", "CLIP")):
         if p not in sys.path:
