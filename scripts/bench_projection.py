@@ -1,5 +1,6 @@
-"""BASELINE.json configs[3]: projection-only sweep (fixed N per cluster, 6 / 10 views) against the
-measured HBM peak.  Algorithmic bytes per cluster = 12 N + V * 224*224*2."""
+"""BASELINE.json configs[3]: projection-only sweep (fixed N per cluster, 6 / 10 views, R = 112 / 224)
+against the measured HBM peak.  Algorithmic bytes per cluster = 12 N + V * 224*224*2.
+Usage: python scripts/bench_projection.py [quick]"""
 import json, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,9 +10,10 @@ from vilgod_b200.engine import Engine
 peaks = json.load(open("MEASURED_PEAKS.json")) if os.path.exists("MEASURED_PEAKS.json") else {"hbm_gbs": 6650.0}
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 rows = []
-for V in (6, 10):
-    eng = Engine(num_views=V)
-    for N in (256, 1024, 4096, 16384, 65536, "waymo"):
+quick = "quick" in sys.argv or "one" in sys.argv
+for V, R in ((10, 112),) if quick else ((6, 112), (10, 112), (6, 224), (10, 224)):
+    eng = Engine(num_views=V, resolution=R)
+    for N in (("waymo",) if "one" in sys.argv else ("waymo", 256, 1024, 4096) if quick else (256, 1024, 4096, 16384, 65536, "waymo")):
         if N == "waymo":
             pts, off = synthetic.make_clusters(3000, n_min=10, n_max=2048, seed=3)
         else:
@@ -20,7 +22,7 @@ for V in (6, 10):
             pts, off = synthetic.make_clusters(C, n_min=N, n_max=N, seed=N)
         C = len(off) - 1
         d_p, d_o = torch.from_numpy(pts).cuda(), torch.from_numpy(off).cuda()
-        tiles = torch.empty((C * V, 196, 256), dtype=torch.bfloat16, device="cuda")
+        tiles = torch.empty((C * V, 196, 256), dtype=eng.op_torch_dtype, device="cuda")
         import ctypes as Cc
         from vilgod_b200.engine import _ptr, _stream
         def run():
@@ -36,7 +38,7 @@ for V in (6, 10):
         ms = float(np.median(ts))
         bytes_alg = 12.0 * int(off[-1]) + C * V * 100352.0
         gbs = bytes_alg / (ms * 1e-3) / 1e9
-        rows.append(dict(views=V, points_per_cluster=N, clusters=C, images=C * V, ms=ms,
+        rows.append(dict(views=V, resolution=R, points_per_cluster=N, clusters=C, images=C * V, ms=ms,
                          us_per_image=1e3 * ms / (C * V), algorithmic_GBs=gbs,
                          frac_of_measured_hbm_peak=gbs / peaks["hbm_gbs"]))
         print(json.dumps(rows[-1]), flush=True)

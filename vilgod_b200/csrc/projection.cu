@@ -301,6 +301,28 @@ template <bool SMEM> __device__ __forceinline__ float img_ld(const float *p)
     return __ldcg(p);
 }
 
+// a / b for 0 <= a < 2^15, 1 <= b <= 512 without the ~25-instruction integer division:
+// floor((a + 0.5) / b) never crosses an integer, and the approximate reciprocal is good to 2 ulp
+__device__ __forceinline__ int small_div(int a, int b)
+{
+    return __float2int_rz(__fdividef((float)a + 0.5f, (float)b));
+}
+
+// f(row, strip) over rows [r0, r1] x strips [s0, s1]: a warp per row, a lane per strip.  R = 112 has
+// 28 strips, so a lane sees at most one strip of a row and the inner loop disappears.
+template <int R, class F>
+__device__ __forceinline__ void for_rows_strips(int r0, int r1, int s0, int s1, int warp, int lane, F f)
+{
+    if (R == 112) {
+        const int s = s0 + lane;
+        if (s <= s1)
+            for (int r = r0 + warp; r <= r1; r += NW) f(r, s);
+    } else {
+        for (int r = r0 + warp; r <= r1; r += NW)
+            for (int s = s0 + lane; s <= s1; s += 32) f(r, s);
+    }
+}
+
 // 3x3 Gaussian (zero padding) of three pooled rows as a row-major FMA chain -- the summation order
 // the oracle uses -- for the four pixels of one strip; t*[0] / t*[5] are the neighbouring columns
 __device__ __forceinline__ void gauss4(const float (&w)[9], const float (&ta)[6], const float (&tb)[6],
@@ -520,12 +542,9 @@ __global__ void __launch_bounds__(NT, R == 112 ? 2 : 1) projection_kernel(const 
     }
     // IMG starts at 0 == max over the empty slices (their smoothed image is identically 0); the
     // dense pass writes whole rows, the stamp pass only inside [ns_lo, ns_hi]
-    {
-        const int s0 = stamp ? ns_lo : 0, s1 = stamp ? ns_hi : NS - 1;
-        for (int r = nlo + warp; r <= nhi; r += NW)
-            for (int s = s0 + lane; s <= s1; s += 32)
-                img_st4<ISM>(IMG + r * R + 4 * s, make_float4(0.f, 0.f, 0.f, 0.f));
-    }
+    for_rows_strips<R>(nlo, nhi, stamp ? ns_lo : 0, stamp ? ns_hi : NS - 1, warp, lane, [&](int r, int s) {
+        img_st4<ISM>(IMG + r * R + 4 * s, make_float4(0.f, 0.f, 0.f, 0.f));
+    });
     if (!stamp)       // dense path: the one clear of the grid buffer
         for (int i = tid; i < R * R / 4; i += NT)
             reinterpret_cast<float4 *>(sm.G)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -534,18 +553,35 @@ __global__ void __launch_bounds__(NT, R == 112 ? 2 : 1) projection_kernel(const 
 
     // ---- background: every output group outside the active rows x groups is a copy of the
     // precomputed background tile; issued now so that the stores drain behind the stencil work ----
+    // The tile is [196 patches][32 x 16 bytes]: a warp copies one whole patch (512 contiguous bytes) per
+    // step, lane = (row inside the patch) * 2 + (half of the 16-pixel row); patches advance by 16 = one
+    // patch row (14) + 2.
     {
-#pragma unroll 4
-        for (int idx = tid; idx < S * NG; idx += NT) {
-            const int oy = idx / NG, g = idx - oy * NG;
-            if (oy >= oy_lo && oy <= oy_hi && g >= g_lo && g <= g_hi) continue;
-            const int patch = (oy >> 4) * 14 + (g >> 1);
-            const int inner = (oy & 15) * 16 + (g & 1) * 8;
-            if (tile)
-                *reinterpret_cast<uint4 *>(tile + patch * 256 + inner) =
-                    __ldg(&tab->bg_tile[(patch * 256 + inner) >> 3]);
-            if (u8)
-                *reinterpret_cast<uint2 *>(u8 + oy * S + 8 * g) = __ldg(&tab->bg_u8[(oy * S + 8 * g) >> 3]);
+        // lane-constant part of the activity test: oy = 16 py + ky in [oy_lo, oy_hi], g = 2 px + half in
+        // [g_lo, g_hi]  <=>  py in [py_lo, py_hi] and px in [px_lo, px_hi] for this lane
+        const int ky = lane >> 1, half = lane & 1;
+        const int py_lo = (oy_lo - ky + 15) >> 4, py_hi = (oy_hi - ky) >> 4;     // arithmetic shifts: floor
+        const int px_lo = (g_lo - half + 1) >> 1, px_hi = (g_hi - half) >> 1;
+        if (tile) {
+            const uint4 *__restrict__ src = tab->bg_tile + lane;
+            uint4 *dst = reinterpret_cast<uint4 *>(tile) + lane;
+            int py = warp >= 14 ? 1 : 0, px = warp >= 14 ? warp - 14 : warp;
+#pragma unroll 13
+            for (int p = warp; p < 196; p += NW) {
+                if (py < py_lo || py > py_hi || px < px_lo || px > px_hi) dst[p * 32] = __ldg(src + p * 32);
+                px += 2; py += 1;
+                if (px >= 14) { px -= 14; py += 1; }
+            }
+        }
+        if (u8) {
+            int py = warp >= 14 ? 1 : 0, px = warp >= 14 ? warp - 14 : warp;
+            for (int p = warp; p < 196; p += NW) {
+                const int oy = py * 16 + ky, g = px * 2 + half;
+                if (py < py_lo || py > py_hi || px < px_lo || px > px_hi)
+                    *reinterpret_cast<uint2 *>(u8 + oy * S + 8 * g) = __ldg(&tab->bg_u8[(oy * S + 8 * g) >> 3]);
+                px += 2; py += 1;
+                if (px >= 14) { px -= 14; py += 1; }
+            }
         }
     }
 
@@ -565,9 +601,9 @@ __global__ void __launch_bounds__(NT, R == 112 ? 2 : 1) projection_kernel(const 
             const int py0 = max(ylo - 3, 0), py1 = min(yhi + 1, Q - 1);       // rows a stamp reaches
             const int ns = gs_hi - gs_lo + 1;
             // clear exactly the pooled cells this slice's Gaussian reads
-            for (int r = py0 + warp; r <= py1; r += NW)
-                for (int s = gs_lo + lane; s <= gs_hi; s += 32)
-                    reinterpret_cast<float4 *>(sm.G + r * R)[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for_rows_strips<R>(py0, py1, gs_lo, gs_hi, warp, lane, [&](int r, int s) {
+                reinterpret_cast<float4 *>(sm.G + r * R)[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+            });
             __syncthreads();
             // stamp: one item = one row of one point's 5x5 footprint.  Pooled pixel (q, x) covers raw
             // cells (q-1..q+3, x-1..x+3), so a point at (Y, X) reaches q in [Y-3, Y+1], x in [X-3, X+1].
@@ -590,11 +626,11 @@ __global__ void __launch_bounds__(NT, R == 112 ? 2 : 1) projection_kernel(const 
             // segments of `own` strips plus one halo lane on each side (neighbours come by shuffle),
             // rpw segment-rows share a warp.
             {
-                const int nseg = (ns + 29) / 30;
-                const int own = (ns + nseg - 1) / nseg;
+                const int nseg = ns > 30 ? 2 : 1;                    // R = 112: always 1 (ns <= 28)
+                const int own = nseg == 1 ? ns : (ns + 1) >> 1;
                 const int lw = own + 2;
-                const int rpw = 32 / lw;
-                const int rg = lane / lw, j = lane - rg * lw;
+                const int rpw = small_div(32, lw);
+                const int rg = small_div(lane, lw), j = lane - rg * lw;
                 const int tasks = (gy1 - gy0 + 1) * nseg;
                 for (int t0 = warp * rpw; t0 < tasks; t0 += NW * rpw) {
                     const int t = t0 + rg;
@@ -790,11 +826,10 @@ __global__ void __launch_bounds__(NT, R == 112 ? 2 : 1) projection_kernel(const 
     {
         const int us_lo = vlo >> 2, us_hi = vhi >> 2;
         float m = 0.0f;
-        for (int r = ulo + warp; r <= uhi; r += NW)
-            for (int s = us_lo + lane; s <= us_hi; s += 32) {
-                const float4 t = img_ld4<ISM>(IMG + r * R + 4 * s);
-                m = fmaxf(fmaxf(m, fmaxf(t.x, t.y)), fmaxf(t.z, t.w));
-            }
+        for_rows_strips<R>(ulo, uhi, us_lo, us_hi, warp, lane, [&](int r, int s) {
+            const float4 t = img_ld4<ISM>(IMG + r * R + 4 * s);
+            m = fmaxf(fmaxf(m, fmaxf(t.x, t.y)), fmaxf(t.z, t.w));
+        });
         m = warp_max(m);
         if (lane == 0) sm.red[warp] = m;
         __syncthreads();
@@ -806,15 +841,14 @@ __global__ void __launch_bounds__(NT, R == 112 ? 2 : 1) projection_kernel(const 
         __syncthreads();
         const float mx = sm.mx;
         const float rc_mx = __frcp_rn(mx);
-        for (int r = nlo + warp; r <= nhi; r += NW)
-            for (int s = ns_lo + lane; s <= ns_hi; s += 32) {
-                float4 t = img_ld4<ISM>(IMG + r * R + 4 * s);
-                t.x = __fsub_rn(1.0f, div_rn(t.x, mx, rc_mx, false));
-                t.y = __fsub_rn(1.0f, div_rn(t.y, mx, rc_mx, false));
-                t.z = __fsub_rn(1.0f, div_rn(t.z, mx, rc_mx, false));
-                t.w = __fsub_rn(1.0f, div_rn(t.w, mx, rc_mx, false));
-                img_st4<ISM>(IMG + r * R + 4 * s, t);
-            }
+        for_rows_strips<R>(nlo, nhi, ns_lo, ns_hi, warp, lane, [&](int r, int s) {
+            float4 t = img_ld4<ISM>(IMG + r * R + 4 * s);
+            t.x = __fsub_rn(1.0f, div_rn(t.x, mx, rc_mx, false));
+            t.y = __fsub_rn(1.0f, div_rn(t.y, mx, rc_mx, false));
+            t.z = __fsub_rn(1.0f, div_rn(t.z, mx, rc_mx, false));
+            t.w = __fsub_rn(1.0f, div_rn(t.w, mx, rc_mx, false));
+            img_st4<ISM>(IMG + r * R + 4 * s, t);
+        });
         __syncthreads();
         if (P.dbg_dens) {
             float *dd = P.dbg_dens + (size_t)b * Q * Q;
@@ -836,7 +870,7 @@ __global__ void __launch_bounds__(NT, R == 112 ? 2 : 1) projection_kernel(const 
     {
         constexpr int HI_ROWS = GE::HI_ROWS;
         const int ng = g_hi - g_lo + 1, ncols = 8 * ng;
-        const int h_nrl = NT / ncols, h_rl = tid / ncols;       // horizontal pass: row lanes
+        const int h_nrl = small_div(NT, ncols), h_rl = small_div(tid, ncols);   // horizontal pass: row lanes
         const int ox = 8 * g_lo + (tid - h_rl * ncols);
         int cx0 = 0, cx1 = 0;
         float clw0 = 0.f, clw1 = 0.f;
@@ -846,7 +880,7 @@ __global__ void __launch_bounds__(NT, R == 112 ? 2 : 1) projection_kernel(const 
             clw1 = __ldg(&tab->l1[ox]);
             cx1 = cx0 + (cx0 < Q - 1 ? 1 : 0);
         }
-        const int v_nrl = NT / ng, v_rl = tid / ng;             // vertical pass: row lanes
+        const int v_nrl = small_div(NT, ng), v_rl = small_div(tid, ng);         // vertical pass: row lanes
         const int g = g_lo + (tid - v_rl * ng);
         const f32x2 k255 = pack2(255.0f, 255.0f), kmagic = pack2(8388608.0f, 8388608.0f);
         const float scale = __fdiv_rn((float)(Q - 1), (float)(S - 1));

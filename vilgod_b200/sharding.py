@@ -15,6 +15,38 @@ def frames_of_rank(num_frames: int, rank: int, world: int):
     return list(range(rank, num_frames, world))
 
 
+class FrameQueue:
+    """Dynamic frame assignment for one sequence: every rank pulls the next unprocessed frame from a
+    shared counter instead of owning f = r (mod W) up front, so a slower board (the 1000 W cap settles
+    the eight boards of a box at different clocks) simply takes fewer frames and no rank waits for it.
+    The counter lives in the process group's key-value store (one atomic add per pull, served by
+    rank 0's TCPStore over localhost): no collective, nothing on the GPU.  Without a process group the
+    queue degenerates to a local counter.  The first pull of rank r returns frame r, which keeps the
+    start of the sequence identical to the static mod-W assignment (zero_shot_detector.py:365
+    iterates the frames in order)."""
+
+    def __init__(self, num_frames: int, name: str = "frames", store=None, rank: int = 0, world: int = 1):
+        self.n, self.rank, self.world = int(num_frames), rank, world
+        self.key = f"vilgod_b200/{name}"
+        self.store = store
+        self.first = True
+        self.local = 0
+        if store is None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            self.store = dist.distributed_c10d._get_default_store()
+            self.rank, self.world = dist.get_rank(), dist.get_world_size()
+
+    def next(self):
+        """-> next frame index for this rank, or None when the sequence is exhausted."""
+        if self.store is None:
+            f, self.local = self.local, self.local + 1
+            return f if f < self.n else None
+        if self.first:                      # frames 0 .. W-1 are pre-assigned, the counter starts at W
+            self.first = False
+            return self.rank if self.rank < self.n else None
+        f = self.store.add(self.key, 1) - 1 + self.world
+        return f if f < self.n else None
+
+
 def gather_labels(frame_ids, cluster_index, voted_class, voted_score, dst: int = 0):
     """Each rank passes 1-D tensors of equal length (its clusters).  Rank ``dst`` receives the
     concatenation sorted by (frame id, cluster index) as numpy arrays; other ranks get None.

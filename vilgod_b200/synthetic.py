@@ -75,3 +75,20 @@ def concat_frames(frames):
         base += int(o[-1])
         bounds.append(bounds[-1] + len(o) - 1)
     return pts, np.concatenate(offs).astype(np.int32), np.asarray(bounds, dtype=np.int64)
+
+
+def make_sequence_raw(num_frames, clusters_per_frame=150, n_min=10, n_max=2048, seed=DEFAULT_SEED):
+    """One fixed sequence in the form the classification loop receives it (zero_shot_detector.py:365,
+    389-393): per frame the RAW fp32 cluster points in the sensor frame, their packed offsets and the
+    frame's 4x4 transform_to_ego -- canonicalisation still to be done.  Deterministic in (seed, frame)."""
+    frames = []
+    for f in range(num_frames):
+        rng = np.random.default_rng([seed, 7919, f])
+        c = max(1, int(rng.poisson(clusters_per_frame)))
+        pts, off, _ = make_clusters_raw(c, n_min, n_max, rng=rng)
+        a = rng.uniform(-np.pi, np.pi)
+        T = np.eye(4)
+        T[:2, :2] = [[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]]
+        T[:3, 3] = rng.uniform(-2.0, 2.0, size=3)
+        frames.append((pts, off, T))
+    return frames
