@@ -224,6 +224,33 @@ def run_reference_arm(a):
     emit_result(line)
 
 
+def cublas_sustained_tflops(seconds=2.0):
+    """Library context for `roofline`: torch.matmul (cuBLAS) 8192^3 back to back for `seconds` per dtype,
+    measured on THIS board right after the timed steps (same power state) -- the recipe behind
+    MEASURED_PEAKS.json's bf16_tflops_sustained, repeated for fp16 because the default build computes
+    in fp16 and fp16 multipliers draw more power under the 1000 W cap than bf16 ones."""
+    import torch
+    out = {}
+    for name, dt in (("f16", torch.float16), ("bf16", torch.bfloat16)):
+        a = torch.randn(8192, 8192, device="cuda", dtype=dt)
+        b = torch.randn(8192, 8192, device="cuda", dtype=dt)
+        for _ in range(3):
+            a @ b
+        torch.cuda.synchronize()
+        n, t0 = 0, time.perf_counter()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        while time.perf_counter() - t0 < seconds:
+            for _ in range(20):
+                a @ b
+            n += 20
+            torch.cuda.current_stream().synchronize()
+        e.record()
+        torch.cuda.synchronize()
+        out[name] = 2.0 * 8192 ** 3 * n / (s.elapsed_time(e) * 1e-3) / 1e12
+    return out
+
+
 def parity_against_golden(operand_dtype):
     """Top-1 agreement of the TIMED build with the unmodified reference, on the committed golden runs
     (tests/golden/e2e.npz: BASELINE configs[0]; e2e_cfg2.npz: a 96-cluster slice of configs[1]):
@@ -513,6 +540,8 @@ def run_ours(a):
     barrier()
     prof = eng.profile_end()
 
+    cublas_ref = cublas_sustained_tflops() if (rank == 0 and world == 1 and not a.no_cpu_baseline) else None
+
     # --- timed region 3: end to end through the host-buffer call ---
     step_e2e()
     barrier()
@@ -557,7 +586,9 @@ def run_ours(a):
                     "achieved": gemm_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": gemm_tflops / peaks["bf16_tflops"], "traffic": traffic,
                     "peak_source": peaks["source"], "launches": g_n,
-                    "avg_launch_ms": g_ms / max(g_n, 1), "share_of_step": g_ms / max(all_ms, 1e-9)}
+                    "avg_launch_ms": g_ms / max(g_n, 1), "share_of_step": g_ms / max(all_ms, 1e-9),
+                    "operand_dtype": a.operand_dtype,
+                    "cublas_sustained_tflops_this_board": cublas_ref}
         p = prof["projection"]
         proj_bytes = p["work"] + 12.0 * total_points * a.steps
         proj_gbs = proj_bytes / (p["ms"] * 1e-3) / 1e9 if p["ms"] > 0 else 0.0
@@ -569,9 +600,13 @@ def run_ours(a):
         ptraffic = None
         tp = os.path.join(ROOT, "profiles", "r02_projection_traffic.json")
         if os.path.exists(tp):
-            ptraffic = json.load(open(tp)).get("dram_bytes_per_launch")
-            roofline_proj["traffic"] = ptraffic
-            roofline_proj["traffic_note"] = json.load(open(tp)).get("note")
+            tj = json.load(open(tp))
+            # ncu measured one launch of 30000 images; the step launches 4090-cluster chunks: scale per image
+            per_image = tj["dram_bytes_per_image"]
+            roofline_proj["traffic"] = per_image * C * V * a.steps / max(p["launches"], 1)
+            roofline_proj["traffic_note"] = (f"{per_image:.0f} B of DRAM traffic per image from one ncu --set full "
+                                             f"capture (profiles/r02_projection_traffic.json) x images per launch")
+            ptraffic = per_image * Cp * V
         pa_gbs = proj_alone_bytes / (proj_alone_ms * 1e-3) / 1e9
         roofline_proj_alone = {"bound": "hbm", "kernel": "projection_kernel, timed alone (burst clocks)",
                                "achieved": pa_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",

@@ -26,11 +26,13 @@ bool env_on(const char *name)
 }
 
 struct EncodeBuffers {
-    float *x;               // residual stream fp32 [M,768]
+    float *x;      // plain tower: residual stream fp32 [M,768].  Folded tower: its first half holds the
+                   // lo plane of the residual stream (operand type [M,768])
     op_t *y;       // attention output (A of out-proj) [M,768]; LayerNorm output when unfused
-    op_t *big;     // qkv [M,2304] / MLP hidden [M,3072]
-    op_t *xb;      // bf16 copy of the residual stream (A of the LayerNorm-folded GEMMs)
-    float *stats;           // row sum / sum of squares of the residual stream [M,3,2]
+    op_t *big;     // qkv [M,2304] / MLP hidden [M,3072]; folded tower: also the fp32 patch-embedding
+                   // output on its way into ln_pre (free at that time)
+    op_t *xb;      // hi plane of the residual stream = A operand of the LayerNorm-folded GEMMs
+    float *stats;  // row sum / sum of squares of the residual stream [M,3,2]
 };
 
 EncodeBuffers carve(void *ws, int64_t chunk)
@@ -67,15 +69,19 @@ int encode_chunk(VgHandle *h, const op_t *tiles, int64_t n, const EncodeBuffers 
     const int64_t M = n * kTokens;
     int rc;
     GemmArgs g;
-    // patch embedding: [n*196, 256] x [768, 256]^T  (+ b_eff + positional embedding)
-    g = GemmArgs{tiles, w.w_patch, w.patch_bias_pos, eb.x, n * kPatches, kWidth, kPatchK, kEpiPatch};
-    if ((rc = launch_gemm(h, g, st))) return rc;
-    // LayerNorm is folded into the GEMMs (no LayerNorm kernel, no normalised copy in HBM):
-    // residual-producing epilogues emit a bf16 copy of x plus per-row sum / sum of squares, the
-    // QKV and c_fc GEMMs multiply the raw bf16 residual by gamma-scaled weights and normalise in
-    // their epilogue.  VG_LN_UNFUSED=1 selects the separate LayerNorm kernels (A/B, debugging).
+    // LayerNorm is folded into the GEMMs (no LayerNorm kernel, no normalised copy in HBM): the residual
+    // stream lives as two operand-typed planes x = hi + lo, residual-producing epilogues update the
+    // planes in place and emit per-row sum / sum of squares, the QKV and c_fc GEMMs multiply the hi
+    // plane by gamma-scaled weights and normalise in their epilogue.  VG_LN_UNFUSED=1 selects the fp32
+    // residual stream with separate LayerNorm kernels (A/B, debugging).
     const bool unfused = h->sw.ln_unfused;
-    if ((rc = launch_ln_pre(h, eb.x, n, unfused ? nullptr : eb.xb, unfused ? nullptr : eb.stats, st)))
+    op_t *xhi = eb.xb, *xlo = reinterpret_cast<op_t *>(eb.x);
+    float *x32 = unfused ? eb.x : reinterpret_cast<float *>(eb.big);
+    // patch embedding: [n*196, 256] x [768, 256]^T  (+ b_eff + positional embedding)
+    g = GemmArgs{tiles, w.w_patch, w.patch_bias_pos, x32, n * kPatches, kWidth, kPatchK, kEpiPatch};
+    if ((rc = launch_gemm(h, g, st))) return rc;
+    if ((rc = launch_ln_pre(h, x32, n, unfused ? nullptr : xhi, unfused ? nullptr : xlo,
+                            unfused ? nullptr : eb.stats, st)))
         return rc;
     const int stop = dbg ? dbg->stop_after_layer : -1;
     bool stopped = stop == -2;
@@ -85,40 +91,46 @@ int encode_chunk(VgHandle *h, const op_t *tiles, int64_t n, const EncodeBuffers 
             if ((rc = launch_layernorm_bf16(h, eb.x, L.ln1_w, L.ln1_b, M, eb.y, st))) return rc;
             g = GemmArgs{eb.y, L.w_qkv, L.b_qkv, eb.big, M, 3 * kWidth, kWidth, VG_EPI_BIAS_BF16};
         } else {
-            g = GemmArgs{eb.xb, L.wf_qkv, L.c_qkv, eb.big, M, 3 * kWidth, kWidth, VG_EPI_BIAS_BF16};
+            g = GemmArgs{xhi, L.wf_qkv, L.c_qkv, eb.big, M, 3 * kWidth, kWidth, VG_EPI_BIAS_BF16};
             g.stats = eb.stats;
             g.colsum = L.s_qkv;
         }
         if ((rc = launch_gemm(h, g, st))) return rc;
         if ((rc = launch_attention(h, eb.big, n, eb.y, st))) return rc;
-        g = GemmArgs{eb.y, L.w_out, L.b_out, eb.x, M, kWidth, kWidth, VG_EPI_BIAS_RESID_F32};
+        g = GemmArgs{eb.y, L.w_out, L.b_out, unfused ? (void *)eb.x : (void *)xlo, M, kWidth, kWidth,
+                     VG_EPI_BIAS_RESID_F32};
         if (!unfused) {
             g.stats = eb.stats;
-            g.xb_out = eb.xb;
+            g.xb_out = xhi;
         }
         if ((rc = launch_gemm(h, g, st))) return rc;
         if (unfused) {
             if ((rc = launch_layernorm_bf16(h, eb.x, L.ln2_w, L.ln2_b, M, eb.y, st))) return rc;
             g = GemmArgs{eb.y, L.w_fc, L.b_fc, eb.big, M, kMlp, kWidth, VG_EPI_BIAS_QGELU_BF16};
         } else {
-            g = GemmArgs{eb.xb, L.wf_fc, L.c_fc, eb.big, M, kMlp, kWidth, VG_EPI_BIAS_QGELU_BF16};
+            g = GemmArgs{xhi, L.wf_fc, L.c_fc, eb.big, M, kMlp, kWidth, VG_EPI_BIAS_QGELU_BF16};
             g.stats = eb.stats;
             g.colsum = L.s_fc;
         }
         if ((rc = launch_gemm(h, g, st))) return rc;
-        g = GemmArgs{eb.big, L.w_proj, L.b_proj, eb.x, M, kWidth, kMlp, VG_EPI_BIAS_RESID_F32};
-        if (!unfused && l + 1 < kLayers && stop != l) {   // the next layer's ln_1 needs xb / stats
+        g = GemmArgs{eb.big, L.w_proj, L.b_proj, unfused ? (void *)eb.x : (void *)xlo, M, kWidth, kMlp,
+                     VG_EPI_BIAS_RESID_F32};
+        if (!unfused) {
             g.stats = eb.stats;
-            g.xb_out = eb.xb;
+            g.xb_out = xhi;
         }
         if ((rc = launch_gemm(h, g, st))) return rc;
         if (stop == l) stopped = true;
     }
-    if (dbg && dbg->d_x)
-        VG_CUDA_CHECK(h, cudaMemcpyAsync(dbg->d_x, eb.x, (size_t)M * kWidth * 4,
-                                         cudaMemcpyDeviceToDevice, st));
+    if (dbg && dbg->d_x) {
+        if (unfused)
+            VG_CUDA_CHECK(h, cudaMemcpyAsync(dbg->d_x, eb.x, (size_t)M * kWidth * 4,
+                                             cudaMemcpyDeviceToDevice, st));
+        else if ((rc = launch_planes_to_f32(h, xhi, xlo, dbg->d_x, M * kWidth, st)))
+            return rc;
+    }
     if (stopped) return VG_OK;
-    return launch_head(h, eb.x, n, probs, top1, feats, logits, st);
+    return launch_head(h, unfused ? eb.x : nullptr, xhi, xlo, n, probs, top1, feats, logits, st);
 }
 
 }  // namespace
@@ -403,12 +415,26 @@ int vg_test_gemm_lnf(VgHandle *h, const void *d_a, const void *d_w, const float 
 {
     if (!h || !d_a || !d_w || !d_bias || !d_out || !d_stats) return VG_EINVAL;
     if (epilogue < 0 || epilogue > VG_EPI_BIAS_RESID_F32) return VG_EINVAL;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
     GemmArgs g{static_cast<const op_t *>(d_a), static_cast<const op_t *>(d_w),
                d_bias, d_out, M, N, K, epilogue};
     g.stats = d_stats;
     g.colsum = d_colsum;
-    g.xb_out = static_cast<op_t *>(d_xb_out);
-    return launch_gemm(h, g, static_cast<cudaStream_t>(stream));
+    if (epilogue != VG_EPI_BIAS_RESID_F32) return launch_gemm(h, g, st);
+    // the tower keeps the residual stream as two operand-typed planes; the hook takes and returns it
+    // as fp32: split -> the production kernel updates the planes in place -> merge
+    if (!d_xb_out) return VG_EINVAL;
+    op_t *lo = nullptr;
+    VG_CUDA_CHECK(h, cudaMalloc(&lo, (size_t)M * N * sizeof(op_t)));
+    op_t *hi = static_cast<op_t *>(d_xb_out);
+    int rc = launch_f32_to_planes(h, static_cast<const float *>(d_out), hi, lo, M * N, st);
+    g.out = lo;
+    g.xb_out = hi;
+    if (!rc) rc = launch_gemm(h, g, st);
+    if (!rc) rc = launch_planes_to_f32(h, hi, lo, static_cast<float *>(d_out), M * N, st);
+    cudaStreamSynchronize(st);
+    cudaFree(lo);
+    return rc;
 }
 
 int vg_test_gemm_patch(VgHandle *h, const void *d_tiles, const void *d_w, const float *d_table,

@@ -193,30 +193,37 @@ struct GemmArgs {
     const op_t *a;   // [M,K]
     const op_t *w;   // [N,K]
     const float *bias;        // [N] (or [197,N] table for the patch-embed epilogue)
-    void *out;                // bf16 [M,N] or fp32 [M,N] (resid: in/out)
+    void *out;                // operand-typed [M,N]; fp32 [M,N] in/out (plain residual epilogue); or the
+                              // lo plane of the residual stream, in/out (LayerNorm-folded residual epilogue)
     int64_t M;
     int32_t N, K;
     int32_t epilogue;         // VG_EPI_* or kEpiPatch
     // LayerNorm folding (2-CTA kernel only; all null = plain epilogues)
     float *stats = nullptr;            // [M][3][2] per column tile: row sum / sum of squares
     const float *colsum = nullptr;     // [N] sum_k W'[n][k]   (bf16 epilogues consuming `stats`)
-    op_t *xb_out = nullptr;   // [M][768] bf16 copy of the new residual (residual epilogue)
+    op_t *xb_out = nullptr;   // [M][768] hi plane of the residual stream, in/out (folded residual epilogue)
 };
 constexpr int kEpiPatch = 3;  // out fp32 x[img*197 + 1 + p][n] = acc + table[1+p][n]
 int launch_gemm(VgHandle *h, const GemmArgs &g, cudaStream_t st);
 // cached cuTensorMapEncodeTiled (SWIZZLE_128B, rank 2 or 3; d0 = innermost extent)
 int make_tmap_nd(VgHandle *h, CUtensorMap *map, CUtensorMapDataType dt, int elt_bytes, const void *ptr,
-                 int rank, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1);
+                 int rank, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1,
+                 int swizzle_bytes = 128);
 
 int launch_attention(VgHandle *h, const op_t *qkv, int64_t B, op_t *out,
                      cudaStream_t st);   // tcgen05 / TMEM (attention_tcgen05.cu)
 int launch_layernorm_bf16(VgHandle *h, const float *x, const float *w, const float *b,
                           int64_t rows, op_t *y, cudaStream_t st);
-// x[img,0,:] = table[0]; then x = LN(x) in place (ln_pre) over all B*197 rows
-int launch_ln_pre(VgHandle *h, float *x, int64_t B, op_t *xb, float *stats, cudaStream_t st);
-// ln_post on CLS rows -> proj -> L2 norm -> logits -> softmax -> argmax
-int launch_head(VgHandle *h, const float *x, int64_t B, float *probs, int32_t *top1, float *feats,
-                float *logits, cudaStream_t st);
+// x[img,0,:] = table[0]; then ln_pre over all B*197 rows of x32.  Plain tower: in place (fp32).
+// LayerNorm-folded tower: the result leaves as the residual planes hi / lo plus row statistics.
+int launch_ln_pre(VgHandle *h, float *x32, int64_t B, op_t *hi, op_t *lo, float *stats, cudaStream_t st);
+// ln_post on CLS rows -> proj -> L2 norm -> logits -> softmax -> argmax; the residual stream is x32
+// (plain tower) or hi + lo (folded tower, x32 == nullptr)
+int launch_head(VgHandle *h, const float *x32, const op_t *hi, const op_t *lo, int64_t B, float *probs,
+                int32_t *top1, float *feats, float *logits, cudaStream_t st);
+// residual planes <-> fp32 (debug tap, test hooks)
+int launch_planes_to_f32(VgHandle *h, const op_t *hi, const op_t *lo, float *x32, int64_t n, cudaStream_t st);
+int launch_f32_to_planes(VgHandle *h, const float *x32, op_t *hi, op_t *lo, int64_t n, cudaStream_t st);
 int launch_vote(VgHandle *h, const float *probs, const int32_t *top1, int32_t C,
                 int32_t *voted_class, float *voted_score, cudaStream_t st);
 int convert_weights(VgHandle *h, const VgVitWeights *w, cudaStream_t st);

@@ -39,8 +39,11 @@ constexpr int SLAB_BYTES = 4096;              // 32 rows x 128 B, SWIZZLE_128B
 // bf16 epilogues (bias, QuickGELU) are instruction-bound: 8 warps, two per TMEM lane quarter, each
 // owning half of the 256 columns.  The fp32 residual epilogue is memory-bound: 4 warps.
 // LNF ("LayerNorm folded"):
-//   residual epilogue  : additionally emits a bf16 copy of the new residual stream (the next
-//                        GEMM's A operand) and accumulates per-row sum / sum-of-squares
+//   residual epilogue  : the residual stream lives in HBM as TWO operand-typed planes, x = hi + lo with
+//                        hi = op(x), lo = op(x - hi) (22 significant bits with fp16 planes).  The hi
+//                        plane IS the next GEMM's A operand, so the update reads 4 and writes 4 bytes
+//                        per element (fp32 residual + separate operand copy: 4 + 6); it also
+//                        accumulates per-row sum / sum-of-squares of the new residual
 //   bf16 epilogues     : A is the RAW residual stream in bf16, W carries the LayerNorm gain, and the
 //                        normalisation is applied after the matmul:
 //                        y = rstd_i * (acc - mu_i * colsum_n) + c_n      (model.py:157-163,190-191)
@@ -54,9 +57,9 @@ constexpr int SLAB_BYTES = 4096;              // 32 rows x 128 B, SWIZZLE_128B
 enum : int { kNarrow = 0, kWide = 1, kDeep = 2 };
 template <int EPI, bool LNF, int RMODE = kNarrow> struct EpiCfg {
     static constexpr bool kResid = EPI == VG_EPI_BIAS_RESID_F32;
-    static constexpr bool kSlim = RMODE != kNarrow;          // 2 in + 1 out + 1 bf16 out per warp
+    static constexpr bool kSlim = RMODE != kNarrow || LNF;   // 2 in + 2 out slabs (4 KB each) per warp
     static constexpr int kWarps = kResid ? (RMODE == kWide ? 8 : 4) : 8;
-    static constexpr int kSlabs = kResid ? (kSlim ? 4 : 2 + 2 + (LNF ? 2 : 0)) : 2;
+    static constexpr int kSlabs = kResid ? (kSlim ? 4 : 2 + 2) : 2;
     static constexpr int kThreads = 64 + 32 * kWarps;
     static constexpr int kStages = kResid ? (RMODE == kWide ? 3 : RMODE == kDeep ? 5 : 4) : 5;
     static constexpr int kEpiBytes = kWarps * kSlabs * SLAB_BYTES;          // 64 / 96 / 128 KiB
@@ -82,11 +85,22 @@ __device__ __forceinline__ float quick_gelu(float v)
 }
 // 16-byte chunk c of row r inside a 1024-byte-aligned SWIZZLE_128B slab
 __device__ __forceinline__ uint32_t slab_off(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
+// 16-byte chunk c (0..3) of the 64-byte row r inside a SWIZZLE_64B slab (32 rows x 32 operands, 2 KB)
+__device__ __forceinline__ uint32_t slab_off64(int r, int c) { return r * 64 + ((c ^ ((r >> 1) & 3)) << 4); }
+__device__ __forceinline__ float2 unpack_op2(uint32_t u)
+{
+#ifndef VG_OPERAND_BF16
+    return __half22float2(*reinterpret_cast<const __half2 *>(&u));
+#else
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&u));
+#endif
+}
 
 template <int EPI, bool LNF, int RMODE, bool PATCH>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<EPI, LNF, RMODE>::kThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
              const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_xb,
+             const __grid_constant__ CUtensorMap tma_hi_in, const __grid_constant__ CUtensorMap tma_lo_in,
              const Params p)
 {
     using Cfg = EpiCfg<EPI, LNF, RMODE>;
@@ -128,6 +142,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         ptx::prefetch_tensormap(&tma_b);
         ptx::prefetch_tensormap(&tma_out);
         if (EPI == VG_EPI_BIAS_RESID_F32 && (LNF || PATCH)) ptx::prefetch_tensormap(&tma_xb);
+        if (EPI == VG_EPI_BIAS_RESID_F32 && LNF) {
+            ptx::prefetch_tensormap(&tma_hi_in);
+            ptx::prefetch_tensormap(&tma_lo_in);
+        }
         for (int s = 0; s < STAGES; ++s) {
             ptx::mbar_init(&full_bar[s], 1);
             ptx::mbar_init(&empty_bar[s], 1);
@@ -230,13 +248,101 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             const int col0 = n_blk * BN;
             const uint32_t tbase = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(as * BN);
 
-            if (EPI == VG_EPI_BIAS_RESID_F32) {
-                // fp32 residual stream in chunks of 32 columns; the x chunk one ahead is in flight while
-                // chunk j is combined.  Narrow: one warp per lane quarter takes all 8 chunks, slabs
-                // [0,2) = x in, 2,3 = x out, 4,5 = bf16 out.  Slim (wide / deep): slabs [0,2) = x in,
-                // 2 = x out, 3 = bf16 out; wide: two warps per quarter take 4 chunks each.
+            if (EPI == VG_EPI_BIAS_RESID_F32 && LNF) {
+                // Residual stream as two operand-typed planes (hi, lo), updated in place in chunks of 32
+                // columns; the planes of the chunk after next are in flight while chunk c is combined.
+                // Per warp (16 KB): [0,4K) = hi|lo in, buffer 0; [4K,8K) = buffer 1 (2 KB SWIZZLE_64B
+                // slabs: 32 rows x 32 operands); [8K,12K) hi out, [12K,16K) lo out (32 rows x 64 operands,
+                // SWIZZLE_128B, one TMA store per plane and PAIR of chunks).  Wide: two warps per TMEM
+                // lane quarter take 4 chunks each.
                 constexpr int NCH = WIDE ? 4 : BN / 32;
-                constexpr int OUT0 = XIN, XB0 = SLIM ? XIN + 1 : XIN + 2;
+                const int ch0 = WIDE ? chalf * NCH : 0;
+                auto issue_in = [&](int buf, int ch) {
+                    ptx::mbar_arrive_expect_tx(&xbar[buf], 2 * 2048);
+                    ptx::tma_load_2d(slab + buf * 4096, &tma_hi_in, &xbar[buf], col0 + ch * 32, row0);
+                    ptx::tma_load_2d(slab + buf * 4096 + 2048, &tma_lo_in, &xbar[buf], col0 + ch * 32, row0);
+                };
+                if (lane == 0) {
+                    issue_in(0, ch0);
+                    issue_in(1, ch0 + 1);
+                }
+                ptx::mbar_wait(&tmem_full[as], aphase);
+                ptx::tc_fence_after();
+                float rs = 0.0f, rq = 0.0f;      // row sum / sum of squares of the new residual
+                unsigned char *hi_out = slab + 2 * SLAB_BYTES, *lo_out = slab + 3 * SLAB_BYTES;
+#pragma unroll 1
+                for (int c = 0; c < NCH; ++c) {
+                    const int ch = ch0 + c;
+                    const int ib = c & 1;
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32b_x32(tbase + (uint32_t)(ch * 32), r);
+                    // the out slabs about to be overwritten must have been drained by their TMA stores
+                    if (ib == 0 && lane == 0) ptx::tma_store_wait_read<0>();
+                    __syncwarp();
+                    ptx::mbar_wait(&xbar[ib], (xphase >> ib) & 1u);
+                    xphase ^= 1u << ib;
+                    ptx::tmem_ld_wait();
+                    const unsigned char *hin = slab + ib * 4096, *lin = hin + 2048;
+                    const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + col0 + ch * 32);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t off = slab_off64(lane, q);
+                        const uint4 h8 = *reinterpret_cast<const uint4 *>(hin + off);
+                        const uint4 l8 = *reinterpret_cast<const uint4 *>(lin + off);
+                        const float4 ba = __ldg(b4 + 2 * q), bb = __ldg(b4 + 2 * q + 1);
+                        const uint32_t hw[4] = {h8.x, h8.y, h8.z, h8.w}, lw[4] = {l8.x, l8.y, l8.z, l8.w};
+                        const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+                        uint32_t ho[4], lo[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 xh = unpack_op2(hw[j]), xl = unpack_op2(lw[j]);
+                            const float o0 = (xh.x + xl.x) + (__uint_as_float(r[8 * q + 2 * j]) + bv[2 * j]);
+                            const float o1 = (xh.y + xl.y) + (__uint_as_float(r[8 * q + 2 * j + 1]) + bv[2 * j + 1]);
+                            rs += o0 + o1;
+                            rq += o0 * o0 + o1 * o1;
+                            ho[j] = pack_op(o0, o1);
+                            const float2 nh = unpack_op2(ho[j]);
+                            lo[j] = pack_op(o0 - nh.x, o1 - nh.y);
+                        }
+                        const uint32_t oo = slab_off(lane, ib * 4 + q);
+                        *reinterpret_cast<uint4 *>(hi_out + oo) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
+                        *reinterpret_cast<uint4 *>(lo_out + oo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (c + 2 < NCH) issue_in(ib, ch + 2);   // refill the planes this chunk has just consumed
+                        if (ib == 1) {
+                            ptx::tma_store_2d(&tma_xb, hi_out, col0 + (ch - 1) * 32, row0);
+                            ptx::tma_store_2d(&tma_out, lo_out, col0 + (ch - 1) * 32, row0);
+                            ptx::tma_store_commit();
+                        }
+                    }
+                }
+                if (WIDE) {     // the column-half partner's partial sums, added in fixed order
+                    float2 *xs = reinterpret_cast<float2 *>(xstat) + lane_base + lane;
+                    if (chalf == 1) *xs = make_float2(rs, rq);
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + ew) : "memory");
+                    if (chalf == 0) {
+                        const float2 o = *xs;
+                        rs += o.x;
+                        rq += o.y;
+                    }
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + ew) : "memory");
+                }
+                const int64_t row = (int64_t)row0 + lane;
+                // one slot per 256-column tile, summed in fixed order by the consumer:
+                // deterministic (no atomics) and nothing to clear between GEMMs
+                if (row < p.M && (!WIDE || chalf == 0))
+                    *reinterpret_cast<float2 *>(p.stats + 6 * row + 2 * n_blk) = make_float2(rs, rq);
+            } else if (EPI == VG_EPI_BIAS_RESID_F32) {
+                // fp32 residual stream in chunks of 32 columns; the x chunk one ahead is in flight while
+                // chunk j is combined (non-folded tower, test hook, and the patch embedding, whose "residual"
+                // is the [197,768] bias / position table).  Narrow: one warp per lane quarter takes all 8
+                // chunks, slabs [0,2) = x in, 2,3 = x out.  Slim (wide / deep): slabs [0,2) = x in, 2 = x
+                // out; wide: two warps per quarter take 4 chunks each.
+                constexpr int NCH = WIDE ? 4 : BN / 32;
+                constexpr int OUT0 = XIN;
                 const int ch0 = WIDE ? chalf * NCH : 0;
                 if (lane == 0) {
 #pragma unroll
@@ -247,7 +353,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                 }
                 ptx::mbar_wait(&tmem_full[as], aphase);
                 ptx::tc_fence_after();
-                float rs = 0.0f, rq = 0.0f;      // row sum / sum of squares of the new residual (LNF)
 #pragma unroll 1
                 for (int c = 0; c < NCH; ++c) {
                     const int ch = ch0 + c;
@@ -272,7 +377,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                     ptx::tmem_ld_wait();
                     const unsigned char *xin = slab + ib * SLAB_BYTES;
                     unsigned char *xout = slab + (OUT0 + (SLIM ? 0 : obuf)) * SLAB_BYTES;
-                    unsigned char *xb = slab + (XB0 + (SLIM ? 0 : ((c >> 1) & 1))) * SLAB_BYTES;
                     const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + col0 + ch * 32);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
@@ -285,14 +389,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                         o.z = x.z + (__uint_as_float(r[4 * q + 2]) + bv.z);
                         o.w = x.w + (__uint_as_float(r[4 * q + 3]) + bv.w);
                         *reinterpret_cast<float4 *>(xout + off) = o;
-                        if (LNF) {
-                            rs += (o.x + o.y) + (o.z + o.w);
-                            rq += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
-                            // bf16 copy: two 32-column chunks share one 64-column slab row (128 B)
-                            uint2 pk = make_uint2(pack_op(o.x, o.y), pack_op(o.z, o.w));
-                            *reinterpret_cast<uint2 *>(xb + slab_off(lane, (c & 1) * 4 + (q >> 1)) +
-                                                       (q & 1) * 8) = pk;
-                        }
                     }
                     ptx::fence_proxy_async();
                     __syncwarp();
@@ -304,29 +400,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                         }
                         if (PATCH) ptx::tma_store_3d(&tma_out, xout, col0 + ch * 32, row0, m_blk);
                         else ptx::tma_store_2d(&tma_out, xout, col0 + ch * 32, row0);
-                        if (LNF && (c & 1))   // same bulk group as this chunk's fp32 store
-                            ptx::tma_store_2d(&tma_xb, xb, col0 + (ch - 1) * 32, row0);
                         ptx::tma_store_commit();
                     }
                     obuf ^= 1;
-                }
-                if (LNF) {
-                    if (WIDE) {     // the column-half partner's partial sums, added in fixed order
-                        float2 *xs = reinterpret_cast<float2 *>(xstat) + lane_base + lane;
-                        if (chalf == 1) *xs = make_float2(rs, rq);
-                        asm volatile("bar.sync %0, 64;" ::"r"(1 + ew) : "memory");
-                        if (chalf == 0) {
-                            const float2 o = *xs;
-                            rs += o.x;
-                            rq += o.y;
-                        }
-                        asm volatile("bar.sync %0, 64;" ::"r"(1 + ew) : "memory");
-                    }
-                    const int64_t row = (int64_t)row0 + lane;
-                    // one slot per 256-column tile, summed in fixed order by the consumer:
-                    // deterministic (no atomics) and nothing to clear between GEMMs
-                    if (row < p.M && (!WIDE || chalf == 0))
-                        *reinterpret_cast<float2 *>(p.stats + 6 * row + 2 * n_blk) = make_float2(rs, rq);
                 }
             } else {
                 // bf16 output: this warp's half of the tile in 2 chunks of 64 columns,
@@ -415,10 +491,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
 // caller's workspace keep their addresses from one launch to the next, so after the first chunk a
 // launch costs a table lookup instead of three or four cuTensorMapEncodeTiled calls.
 int make_tmap_nd(VgHandle *h, CUtensorMap *map, CUtensorMapDataType dt, int elt_bytes, const void *ptr,
-                 int rank, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1)
+                 int rank, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1,
+                 int swizzle_bytes)
 {
     const uint64_t key[6] = {reinterpret_cast<uint64_t>(ptr), d0, d1, d2,
-                             ((uint64_t)box0 << 32) | box1, ((uint64_t)dt << 8) | (uint64_t)rank};
+                             ((uint64_t)box0 << 32) | box1,
+                             ((uint64_t)swizzle_bytes << 16) | ((uint64_t)dt << 8) | (uint64_t)rank};
     for (const VgTmapEntry &e : h->tmaps)
         if (memcmp(e.key, key, sizeof(key)) == 0) {
             *map = e.map;
@@ -434,7 +512,8 @@ int make_tmap_nd(VgHandle *h, CUtensorMap *map, CUtensorMapDataType dt, int elt_
     const cuuint32_t box[3] = {box0, box1, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(map, dt, (cuuint32_t)rank, const_cast<void *>(ptr), gdim, gstride, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         VG_SET_ERR(h, "cuTensorMapEncodeTiled failed (CUresult %d) rank=%d dims=%llu,%llu,%llu", (int)r,
@@ -452,15 +531,15 @@ int make_tmap_nd(VgHandle *h, CUtensorMap *map, CUtensorMapDataType dt, int elt_
 namespace {
 
 int make_tmap(VgHandle *h, CUtensorMap *map, CUtensorMapDataType dt, int elt_bytes, const void *ptr,
-              uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols)
+              uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols, int swizzle_bytes = 128)
 {
-    return make_tmap_nd(h, map, dt, elt_bytes, ptr, 2, cols, rows, 1, box_cols, box_rows);
+    return make_tmap_nd(h, map, dt, elt_bytes, ptr, 2, cols, rows, 1, box_cols, box_rows, swizzle_bytes);
 }
 
 int make_tmap3(VgHandle *h, CUtensorMap *map, CUtensorMapDataType dt, int elt_bytes, const void *ptr,
                uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1)
 {
-    return make_tmap_nd(h, map, dt, elt_bytes, ptr, 3, d0, d1, d2, box0, box1);
+    return make_tmap_nd(h, map, dt, elt_bytes, ptr, 3, d0, d1, d2, box0, box1, 128);
 }
 
 template <int EPI, bool LNF, int RMODE = kNarrow>
@@ -473,17 +552,26 @@ int launch_t(VgHandle *h, const GemmArgs &g, cudaStream_t st)
     rc = make_tmap(h, &tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.w, (uint64_t)g.N, (uint64_t)g.K,
                    BN / 2, BK);
     if (rc) return rc;
-    if (EPI == VG_EPI_BIAS_RESID_F32)
+    if (EPI == VG_EPI_BIAS_RESID_F32 && !LNF)
         rc = make_tmap(h, &to, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.out, (uint64_t)g.M, (uint64_t)g.N,
                        32, 32);
-    else
+    else    // operand-typed output, or (folded residual) the lo plane of the residual stream
         rc = make_tmap(h, &to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.out, (uint64_t)g.M,
                        (uint64_t)g.N, 32, 64);
     if (rc) return rc;
-    txb = to;
+    CUtensorMap thi, tlo;
+    txb = thi = tlo = to;
     if (EPI == VG_EPI_BIAS_RESID_F32 && LNF) {
+        // residual planes, updated in place: hi = g.xb_out, lo = g.out.  Stores per pair of 32-column
+        // chunks (128-byte rows), loads per chunk (64-byte rows, SWIZZLE_64B)
         rc = make_tmap(h, &txb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.xb_out, (uint64_t)g.M,
                        (uint64_t)g.N, 32, 64);
+        if (rc) return rc;
+        rc = make_tmap(h, &thi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.xb_out, (uint64_t)g.M,
+                       (uint64_t)g.N, 32, 32, 64);
+        if (rc) return rc;
+        rc = make_tmap(h, &tlo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.out, (uint64_t)g.M,
+                       (uint64_t)g.N, 32, 32, 64);
         if (rc) return rc;
     }
     using Cfg = EpiCfg<EPI, LNF, RMODE>;
@@ -498,7 +586,8 @@ int launch_t(VgHandle *h, const GemmArgs &g, cudaStream_t st)
                      : EPI == VG_EPI_BIAS_QGELU_BF16 ? VG_K_GEMM_FC
                      : (g.K == kMlp ? VG_K_GEMM_PROJ : VG_K_GEMM_OUT);
     VgProfScope prof(h, kind, 2.0 * (double)g.M * g.N * (double)g.K, st);
-    gemm2_kernel<EPI, LNF, RMODE, false><<<2 * clusters, Cfg::kThreads, Cfg::kSmem, st>>>(ta, tb, to, txb, p);
+    gemm2_kernel<EPI, LNF, RMODE, false><<<2 * clusters, Cfg::kThreads, Cfg::kSmem, st>>>(ta, tb, to, txb, thi,
+                                                                                          tlo, p);
     VG_LAUNCH_CHECK(h);
     return VG_OK;
 }
@@ -535,7 +624,7 @@ int launch_gemm_patch(VgHandle *h, const GemmArgs &g, cudaStream_t st)
     const int clusters = (int)(tiles < max_clusters ? tiles : max_clusters);
     // credited with the un-folded K = 3*16*16
     VgProfScope prof(h, VG_K_GEMM_PATCH, 2.0 * (double)g.M * g.N * 768.0, st);
-    kern<<<2 * clusters, Cfg::kThreads, Cfg::kSmem, st>>>(ta, tb, to, ttab, p);
+    kern<<<2 * clusters, Cfg::kThreads, Cfg::kSmem, st>>>(ta, tb, to, ttab, ttab, ttab, p);
     VG_LAUNCH_CHECK(h);
     return VG_OK;
 }
@@ -560,7 +649,7 @@ int launch_gemm(VgHandle *h, const GemmArgs &g, cudaStream_t st)
         return VG_EINVAL;
     }
     if (lnf && g.epilogue == VG_EPI_BIAS_RESID_F32 && (!g.xb_out || g.N != kWidth)) {
-        VG_SET_ERR(h, "gemm: fused residual epilogue needs xb_out and N = 768");
+        VG_SET_ERR(h, "gemm: folded residual epilogue needs the hi plane (xb_out) and N = 768");
         return VG_EINVAL;
     }
     switch (g.epilogue) {

@@ -30,6 +30,19 @@ struct Row768 {
 #pragma unroll
         for (int i = 0; i < 6; ++i) v[i] = reinterpret_cast<const float4 *>(row)[lane + 32 * i];
     }
+    // residual stream as operand-typed planes: x = hi + lo
+    __device__ __forceinline__ void load_planes(const op_t *hi, const op_t *lo, int lane)
+    {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const uint2 h = reinterpret_cast<const uint2 *>(hi)[lane + 32 * i];
+            const uint2 l = reinterpret_cast<const uint2 *>(lo)[lane + 32 * i];
+            v[i].x = from_op(reinterpret_cast<const op_t *>(&h)[0]) + from_op(reinterpret_cast<const op_t *>(&l)[0]);
+            v[i].y = from_op(reinterpret_cast<const op_t *>(&h)[1]) + from_op(reinterpret_cast<const op_t *>(&l)[1]);
+            v[i].z = from_op(reinterpret_cast<const op_t *>(&h)[2]) + from_op(reinterpret_cast<const op_t *>(&l)[2]);
+            v[i].w = from_op(reinterpret_cast<const op_t *>(&h)[3]) + from_op(reinterpret_cast<const op_t *>(&l)[3]);
+        }
+    }
     __device__ __forceinline__ void normalise(const float *w, const float *b, int lane)
     {
         float s = 0.0f;
@@ -75,12 +88,22 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const float *__rest
         dst[lane + 32 * i] = make_uint2(pack_bf16x2(r.v[i].x, r.v[i].y), pack_bf16x2(r.v[i].z, r.v[i].w));
 }
 
-// x[img][0][:] = class_embedding + pos[0] (table row 0); every row: x = ln_pre(x), fp32 in place
+// split fp32 into the residual planes: hi = op(x), lo = op(x - hi)
+__device__ __forceinline__ void split_planes(float4 v, uint2 &h, uint2 &l)
+{
+    h = make_uint2(pack_op(v.x, v.y), pack_op(v.z, v.w));
+    const op_t *hp = reinterpret_cast<const op_t *>(&h);
+    l = make_uint2(pack_op(v.x - from_op(hp[0]), v.y - from_op(hp[1])),
+                   pack_op(v.z - from_op(hp[2]), v.w - from_op(hp[3])));
+}
+
+// x[img][0][:] = class_embedding + pos[0] (table row 0); every row: ln_pre(x).  Plain tower: fp32 in
+// place.  LayerNorm-folded tower (hi != nullptr): the result leaves as the residual planes + row statistics.
 __global__ void __launch_bounds__(256) ln_pre_kernel(float *__restrict__ x,
                                                      const float *__restrict__ table,
                                                      const float *__restrict__ w,
                                                      const float *__restrict__ b, int64_t rows,
-                                                     op_t *__restrict__ xb,
+                                                     op_t *__restrict__ hi, op_t *__restrict__ lo,
                                                      float *__restrict__ stats)
 {
     const int lane = threadIdx.x & 31;
@@ -89,15 +112,20 @@ __global__ void __launch_bounds__(256) ln_pre_kernel(float *__restrict__ x,
     Row768 r;
     r.load((row % kTokens == 0) ? table : x + row * kWidth, lane);
     r.normalise(w, b, lane);
-    float4 *dst = reinterpret_cast<float4 *>(x + row * kWidth);
+    if (!hi) {
+        float4 *dst = reinterpret_cast<float4 *>(x + row * kWidth);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) dst[lane + 32 * i] = r.v[i];
-    if (xb) {   // LayerNorm-folded tower: bf16 copy of the residual + row sum / sum of squares
-        uint2 *db = reinterpret_cast<uint2 *>(xb + row * kWidth);
+        for (int i = 0; i < 6; ++i) dst[lane + 32 * i] = r.v[i];
+    } else {
+        uint2 *dh = reinterpret_cast<uint2 *>(hi + row * kWidth);
+        uint2 *dl = reinterpret_cast<uint2 *>(lo + row * kWidth);
         float sum = 0.0f, sq = 0.0f;
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-            db[lane + 32 * i] = make_uint2(pack_bf16x2(r.v[i].x, r.v[i].y), pack_bf16x2(r.v[i].z, r.v[i].w));
+            uint2 h, l;
+            split_planes(r.v[i], h, l);
+            dh[lane + 32 * i] = h;
+            dl[lane + 32 * i] = l;
             sum += (r.v[i].x + r.v[i].y) + (r.v[i].z + r.v[i].w);
             sq += (r.v[i].x * r.v[i].x + r.v[i].y * r.v[i].y) + (r.v[i].z * r.v[i].z + r.v[i].w * r.v[i].w);
         }
@@ -112,8 +140,27 @@ __global__ void __launch_bounds__(256) ln_pre_kernel(float *__restrict__ x,
 // softmax (model.py:236-239, clip_utils.py:41-43).  The 1.5 MB projection matrix and the text
 // features are streamed from L2 once per CTA and reused for all its images (one image per CTA made
 // the kernel L2-bandwidth bound); per image the arithmetic and its order are unchanged.
+__global__ void planes_to_f32_kernel(const op_t *__restrict__ hi, const op_t *__restrict__ lo,
+                                     float *__restrict__ x, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = from_op(hi[i]) + from_op(lo[i]);
+}
+__global__ void f32_to_planes_kernel(const float *__restrict__ x, op_t *__restrict__ hi,
+                                     op_t *__restrict__ lo, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const op_t h = to_op(x[i]);
+        hi[i] = h;
+        lo[i] = to_op(x[i] - from_op(h));
+    }
+}
+
 constexpr int kHeadImgs = 8;
 __global__ void __launch_bounds__(256) head_kernel(const float *__restrict__ x,
+                                                   const op_t *__restrict__ xhi,
+                                                   const op_t *__restrict__ xlo,
                                                    const float *__restrict__ lw,
                                                    const float *__restrict__ lb,
                                                    const float *__restrict__ proj,
@@ -135,7 +182,9 @@ __global__ void __launch_bounds__(256) head_kernel(const float *__restrict__ x,
     {   // warp g normalises the class token of image g
         Row768 r;
         if (warp < nimg) {
-            r.load(x + (img0 + warp) * (int64_t)kTokens * kWidth, lane);
+            const int64_t off = (img0 + warp) * (int64_t)kTokens * kWidth;
+            if (x) r.load(x + off, lane);
+            else r.load_planes(xhi + off, xlo + off, lane);
             r.normalise(lw, lb, lane);
         } else {
 #pragma unroll
@@ -382,25 +431,41 @@ int launch_layernorm_bf16(VgHandle *h, const float *x, const float *w, const flo
     return VG_OK;
 }
 
-int launch_ln_pre(VgHandle *h, float *x, int64_t B, op_t *xb, float *stats, cudaStream_t st)
+int launch_ln_pre(VgHandle *h, float *x, int64_t B, op_t *hi, op_t *lo, float *stats, cudaStream_t st)
 {
     const int64_t rows = B * kTokens;
     if (rows <= 0) return VG_OK;
     VgProfScope prof(h, VG_K_LN_PRE, (double)rows * kWidth * 8.0, st);
     ln_pre_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, h->vit.patch_bias_pos,
                                                               h->vit.ln_pre_w, h->vit.ln_pre_b, rows,
-                                                              xb, stats);
+                                                              hi, lo, stats);
     VG_LAUNCH_CHECK(h);
     return VG_OK;
 }
 
-int launch_head(VgHandle *h, const float *x, int64_t B, float *probs, int32_t *top1, float *feats,
-                float *logits, cudaStream_t st)
+int launch_planes_to_f32(VgHandle *h, const op_t *hi, const op_t *lo, float *x32, int64_t n, cudaStream_t st)
+{
+    if (n <= 0) return VG_OK;
+    planes_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(hi, lo, x32, n);
+    VG_LAUNCH_CHECK(h);
+    return VG_OK;
+}
+
+int launch_f32_to_planes(VgHandle *h, const float *x32, op_t *hi, op_t *lo, int64_t n, cudaStream_t st)
+{
+    if (n <= 0) return VG_OK;
+    f32_to_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x32, hi, lo, n);
+    VG_LAUNCH_CHECK(h);
+    return VG_OK;
+}
+
+int launch_head(VgHandle *h, const float *x, const op_t *hi, const op_t *lo, int64_t B, float *probs,
+                int32_t *top1, float *feats, float *logits, cudaStream_t st)
 {
     if (B <= 0) return VG_OK;
     VgProfScope prof(h, VG_K_HEAD, (double)B * kWidth * 4.0, st);
     head_kernel<<<(unsigned)((B + kHeadImgs - 1) / kHeadImgs), 256, 0, st>>>(
-        x, h->vit.ln_post_w, h->vit.ln_post_b, h->vit.proj, h->d_text, h->num_prompts,
+        x, hi, lo, h->vit.ln_post_w, h->vit.ln_post_b, h->vit.proj, h->d_text, h->num_prompts,
         (float)h->cfg.logit_scale, B, probs, top1, feats, logits);
     VG_LAUNCH_CHECK(h);
     return VG_OK;
