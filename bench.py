@@ -306,6 +306,102 @@ def parity_against_golden(operand_dtype):
             "dtype": operand_dtype, **worst, "runs": out}
 
 
+def run_other_configs(a, eng):
+    """The remaining BASELINE.json configurations as extra keys of the N = 1 line, so that none of them
+    rests on a builder-run script alone: configs[0] (one 128-cluster frame, 6 views, host to host),
+    configs[3] (projection-only sweep, alone) and configs[4] (encoder-only, 1k..16k images)."""
+    import torch
+    from vilgod_b200 import synthetic, weights as vw
+    from vilgod_b200.engine import Engine, _ptr, _stream
+    peaks = load_peaks()
+    gold = os.path.join(ROOT, "tests", "golden")
+    out = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    # configs[0]: the golden frame the reference itself was timed on (tests/golden/e2e.npz: ref_seconds)
+    g = np.load(os.path.join(gold, "e2e.npz"))
+    e6 = Engine(num_views=6, operand_dtype=a.operand_dtype)
+    try:
+        e6.load_vit_weights(vw.random_init_visual_state_dict(1234))
+        e6.set_text_features(np.load(os.path.join(gold, "tables.npz"))["text_features"])
+        hp, ho = torch.from_numpy(g["points"]).pin_memory(), torch.from_numpy(g["offsets"]).pin_memory()
+        o6 = e6.alloc_outputs(128, want_feats=False)
+
+        def frame():
+            e6.classify(hp.cuda(non_blocking=True), ho.cuda(non_blocking=True), want_feats=False, out=o6)
+            return o6["voted_class"].cpu(), o6["voted_score"].cpu(), o6["top1"].cpu()
+
+        for _ in range(3):
+            frame()
+        ts = []
+        for _ in range(10):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            frame()
+            ts.append(time.perf_counter() - t0)
+        ms = 1e3 * float(np.median(ts))
+        out["cfg1_single_frame"] = {
+            "workload": "BASELINE configs[0]: one frame, 128 clusters <= 2048 pts, 6 views, pinned host points in, labels out",
+            "ms_per_frame": ms, "clusters_per_second": 128 / (ms * 1e-3),
+            "reference_cpu_seconds_build_container": float(g["ref_seconds"]), "reference_cpu_cores": int(g["ref_cores"])}
+        # configs[4]: encoder only, tiles drawn from that frame's projection
+        base = e6.project(g["points"], g["offsets"])["tiles"]
+        rows = []
+        for B in (1024, 4096, 16384):
+            tiles = base.repeat((B + base.shape[0] - 1) // base.shape[0], 1, 1)[:B].contiguous()
+            e6.encode_score(tiles, want_feats=False)
+            ts = []
+            for _ in range(3):
+                flush.zero_()
+                s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s_.record(); e6.encode_score(tiles, want_feats=False); e_.record()
+                torch.cuda.synchronize()
+                ts.append(s_.elapsed_time(e_))
+            t = float(np.median(ts))
+            tf = FLOP_PER_IMAGE * B / (t * 1e-3) / 1e12
+            rows.append({"images": B, "ms": t, "images_per_second": B / (t * 1e-3), "algorithmic_tflops": tf,
+                         "frac_of_sustained_bf16_peak": tf / peaks["bf16_tflops"]})
+            del tiles
+        out["cfg5_encoder_only"] = {"workload": "BASELINE configs[4]: ViT-B/16 + prompt scoring on B depth images", "rows": rows}
+    finally:
+        e6.close()
+
+    # configs[3]: projection only, fixed N per cluster, R in {112, 224}, timed alone
+    rows = []
+    for R in (112, 224):
+        ep = Engine(num_views=10, resolution=R, operand_dtype=a.operand_dtype)
+        try:
+            for N in (256, 4096, 65536):
+                C = 600 if N <= 4096 else 100
+                pts, off = synthetic.make_clusters(C, n_min=N, n_max=N, seed=N)
+                d_p, d_o = torch.from_numpy(pts).cuda(), torch.from_numpy(off).cuda()
+                tiles = torch.empty((C * 10, 196, 256), dtype=ep.op_torch_dtype, device="cuda")
+
+                def run():
+                    ep._check(ep.lib.vg_project(ep._h, _ptr(d_p), _ptr(d_o), C, _ptr(tiles), None, None, None, _stream()))
+
+                for _ in range(2):
+                    run()
+                ts = []
+                for _ in range(3):
+                    flush.zero_()
+                    s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s_.record(); run(); e_.record()
+                    torch.cuda.synchronize()
+                    ts.append(s_.elapsed_time(e_))
+                t = float(np.median(ts))
+                gbs = (12.0 * int(off[-1]) + C * 10 * 100352.0) / (t * 1e-3) / 1e9
+                rows.append({"resolution": R, "points_per_cluster": N, "clusters": C, "views": 10, "ms": t,
+                             "us_per_image": 1e3 * t / (C * 10), "algorithmic_GBs": gbs,
+                             "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]})
+                del tiles, d_p, d_o
+        finally:
+            ep.close()
+    out["cfg4_projection_only"] = {"workload": "BASELINE configs[3]: projection only, fixed N per cluster, 10 views, "
+                                               "after the tower work (board inside the power cap)", "rows": rows}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # extra keys (never part of `value`): BASELINE.json configs[2] and a fixed sequence, strong scaling
 # ------------------------------------------------------------------------------------------------
@@ -331,6 +427,9 @@ def run_extras(a, eng, rank, world, barrier):
             dist.all_reduce(sm, op=dist.ReduceOp.SUM)
             return float(mx[0]), float(sm[1])
         return ms, float(units)
+
+    if rank == 0 and world == 1:
+        res.update(run_other_configs(a, eng))
 
     if a.cfg3_frames > 0:
         frames = []
@@ -682,6 +781,8 @@ def run_ours(a):
             "vit_tensor_frac_of_peak": vit_frac,
             "images_per_second": C_all * V * a.steps / (ms_total * 1e-3),
             "kernel_breakdown_rank0": breakdown, "clocks": clocks, "cpu_baseline": cpu_baseline,
+            "cfg1_single_frame": extras.get("cfg1_single_frame"), "cfg4_projection_only": extras.get("cfg4_projection_only"),
+            "cfg5_encoder_only": extras.get("cfg5_encoder_only"),
             "cfg3": extras.get("cfg3"), "strong_scaling": extras.get("strong_scaling"),
             "parity": parity, "timed_step_check": {"flagged_clusters": bad,
                                                    "voted_label_histogram_rank0": timed_label_hist},

@@ -1,0 +1,8 @@
+#!/bin/bash
+# Round 2: the evidence set for profiles/ from the final tree: GPU tests, both bench arms, projection sweep.
+mkdir -p gpurun_out
+( python -m pytest tests -q -m gpu 2>&1 | grep -v "Warning\|wrap(\|k3 = \|^$\|Docs:\|warnings summary" | tail -8; python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 ) > gpurun_out/r02_gpu_tests.txt 2>&1
+cat gpurun_out/r02_gpu_tests.txt
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02_bench_reference_arm.json 2> gpurun_out/ref_arm.err; echo "reference arm exit $?"; cut -c1-400 gpurun_out/r02_bench_reference_arm.json
+timeout 1200 python bench.py --steps 3 --warmup 3 > gpurun_out/r02_bench_default.json 2> gpurun_out/bench_default.err; echo "bench exit $?"; tail -3 gpurun_out/bench_default.err
+timeout 600 python scripts/bench_projection.py > gpurun_out/r02_projection_sweep.jsonl 2> gpurun_out/proj_sweep.err; echo "sweep exit $?"; cat gpurun_out/r02_projection_sweep.jsonl | cut -c1-260
