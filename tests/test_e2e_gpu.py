@@ -380,3 +380,53 @@ def test_clip_wrapper_mirror_with_cached_features(golden):
         assert cw.predict_clip_labels([]) == ([], [])
     finally:
         cw.engine.close()
+
+
+def test_full_size_batch_properties(golden):
+    """BASELINE.json configs[1] at FULL size (64 frames x ~300 clusters, 10 views: 188 k images) through
+    vg_classify, checked by size-independent properties: run-to-run bit stability, no flagged cluster,
+    every probability row sums to 1 and its arg-max is the reported top-1, unit-norm embeddings, the GPU
+    vote equals the host mirror of LidarFrame.update_object_classes on the GPU's own per-view results,
+    chunk boundaries leave no trace (a 500-cluster slice classified alone gives the same bits), and a
+    permutation of the points inside every cluster changes nothing (scatter-max is order independent)."""
+    from vilgod_b200 import synthetic, voting, weights
+    from vilgod_b200.engine import Engine
+    frames = []
+    for f in range(64):
+        rng = np.random.default_rng([20240807, f])
+        frames.append(synthetic.make_clusters(max(1, int(rng.poisson(300))), n_min=10, n_max=2048, rng=rng))
+    pts, off, _ = synthetic.concat_frames(frames)
+    C, V = len(off) - 1, 10
+    e = Engine(num_views=V)
+    try:
+        e.load_vit_weights(weights.random_init_visual_state_dict(1234))
+        e.set_text_features(weights.synthetic_text_features(24))
+        d_p, d_o = torch.from_numpy(pts).cuda(), torch.from_numpy(off).cuda()
+        a = e.classify(d_p, d_o)
+        a = {k: v.clone() for k, v in a.items() if v is not None}
+        b = e.classify(d_p, d_o)
+        torch.cuda.synchronize()
+        for k in ("probs", "top1", "feats", "voted_class", "voted_score"):
+            assert torch.equal(a[k], b[k]), k
+        assert int(a["status"].abs().sum()) == 0
+        probs = a["probs"]
+        assert float((probs.sum(dim=-1) - 1).abs().max()) <= 1e-5
+        assert torch.equal(probs.gather(-1, a["top1"].long().unsqueeze(-1)).squeeze(-1), probs.max(dim=-1).values)
+        assert float((a["feats"].norm(dim=-1) - 1).abs().max()) <= 1e-5
+        top1 = a["top1"].cpu().numpy()
+        sc = np.take_along_axis(probs.cpu().numpy(), top1[..., None].astype(np.int64), axis=2)[..., 0]
+        vid, vs = voting.vote(np.asarray(e.class_map)[top1], sc, len(e.mapped_names))
+        assert np.array_equal(vid, a["voted_class"].cpu().numpy())
+        assert np.array_equal(vs, a["voted_score"].cpu().numpy())
+        # a slice that straddles an internal chunk boundary (409 clusters x 10 views per 4096-image chunk)
+        c0, c1 = 4090 - 250, 4090 + 250
+        sub = e.classify(pts[off[c0]:off[c1]], (off[c0:c1 + 1] - off[c0]).astype(np.int32))
+        assert torch.equal(sub["probs"], a["probs"][c0:c1]) and torch.equal(sub["voted_class"], a["voted_class"][c0:c1])
+        # permutation inside clusters (first 2000 clusters)
+        n2 = 2000
+        rng = np.random.default_rng(1)
+        perm = np.concatenate([off[c] + rng.permutation(off[c + 1] - off[c]) for c in range(n2)])
+        pp = e.classify(pts[:off[n2]][perm], off[:n2 + 1])
+        assert torch.equal(pp["probs"], a["probs"][:n2])
+    finally:
+        e.close()
