@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_one_contract_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                        "--warmup", "0", "--cpu-sample-clusters", "2", "--views", "4"],
+                        "--warmup", "0", "--ref-sample-clusters", "2", "--views", "4"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
@@ -27,6 +27,32 @@ def test_reference_arm_prints_one_contract_line():
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    # with the reference tree mounted (or staged under oracle/_ref by oracle/make_ref.py) the arm must run
+    # the unmodified reference loop, not the port
+    from oracle import ref_harness as rh
+    if rh.available():
+        assert cb["kind"] == "reference" and "UNMODIFIED reference" in cb["sample"]
+    assert d["config"]["sample_clusters_per_step"] == 2 and d["gpu_launches"] == 0
+
+
+def test_reference_staging_recipe_copies_only_what_the_path_imports(tmp_path, monkeypatch):
+    """oracle/make_ref.py: byte-for-byte copies of the reference's src/ and clip packages into a git-ignored
+    directory (never into the history), enough for ref_harness to import the hot path from the copy alone."""
+    import filecmp
+    from oracle import make_ref, ref_harness as rh
+    if not os.path.isdir(make_ref.SOURCE_ROOT):
+        import pytest
+        pytest.skip("reference tree not mounted")
+    monkeypatch.setattr(make_ref, "DEST", str(tmp_path / "_ref"))
+    n = make_ref.stage()
+    assert n >= 20
+    for rel in ("src/utils/mv_utils.py", "src/utils/clip_utils.py", "src/vilgod/lidar_frame.py",
+                "third_party/CLIP/clip/model.py", "third_party/CLIP/clip/bpe_simple_vocab_16e6.txt.gz"):
+        assert filecmp.cmp(os.path.join(make_ref.SOURCE_ROOT, rel), str(tmp_path / "_ref" / rel), shallow=False)
+    ignored = open(os.path.join(ROOT, ".gitignore")).read()
+    assert "oracle/_ref/" in ignored
+    gpurunignore = os.path.join(ROOT, ".gpurunignore")
+    assert not os.path.exists(gpurunignore) or "oracle/_ref" not in open(gpurunignore).read()
 
 
 def test_non_zero_ranks_of_the_reference_arm_exit_quietly():

@@ -123,6 +123,9 @@ def test_residual_gemm_variants_emit_copy_and_statistics(eng, M, K):
     w = (torch.randn(N, K, device="cuda", generator=g) * (K ** -0.5)).to(eng.op_torch_dtype)
     b = torch.randn(N, device="cuda", generator=g)
     x0 = torch.randn(M, N, device="cuda", generator=g) + 0.3
+    if M < 2000:         # massive-activation channels, as real CLIP residual streams carry
+        x0[:, 17] += 250.0
+        x0[:, 403] -= 120.0
     stats = torch.full((M, 3, 2), float("nan"), device="cuda")
     x, xb = eng.test_gemm_lnf(a, w, b, 2, stats, x_inout=x0.clone())
     # the planes hold x0 to 2^-22 (fp16) / 2^-16 (bf16) relative before the update and x after it
@@ -133,7 +136,7 @@ def test_residual_gemm_variants_emit_copy_and_statistics(eng, M, K):
     assert (xb != x.to(eng.op_torch_dtype)).float().mean().item() < 1e-3
     assert (xb.float() - x).abs().max().item() <= _ulp(eng) * x.abs().max().item()
     rs = _row_stats(x)
-    assert torch.allclose(stats, rs, rtol=3e-5, atol=2e-3)        # fp32 sums of 256 terms, other order
+    assert torch.allclose(stats, rs, rtol=3e-5, atol=2e-3 + 2e-6 * rs.abs().max().item())   # fp32 sums of 256 terms, other order
 
 
 @pytest.mark.parametrize("B", [1, 5, 300])
