@@ -43,7 +43,8 @@ for r, l in zip(sass, lines_of):
 ti, ts = sum(inst.values()), sum(samp.values())
 src = {}
 print(f"total warp instructions {ti}, stall samples {ts}")
-for l, n in inst.most_common(top):
+for l, n in (samp.most_common(top) if os.environ.get('VG_BY_STALL') else inst.most_common(top)):
+    n = inst[l]
     if l and l[0] not in src:
         p = os.path.join(os.path.dirname(os.path.abspath(lib)), "..", "csrc", l[0])
         src[l[0]] = open(p).read().splitlines() if os.path.exists(p) else []

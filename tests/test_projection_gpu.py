@@ -157,6 +157,57 @@ def test_stamp_and_dense_paths_agree(engines):
         assert np.array_equal(a["u8"].cpu().numpy().reshape(u8_o.shape), u8_o)
 
 
+def test_fast_and_general_kernels_agree(monkeypatch):
+    """The fast kernel (register-resident image, bounding-box buffer, walking emit; clusters up to 2048
+    points) hands larger clusters over to the general kernel in list mode.  Every variant of it
+    (VG_PROJ_VARIANT 1 / 2 / 3) must produce the bits of the general kernel alone (variant 0) and of the
+    oracle, for tiles, uint8 (all views and first view only) and the densified tap."""
+    from vilgod_b200 import synthetic
+    from vilgod_b200.engine import Engine
+    rng = np.random.default_rng(77)
+    pts, off = synthetic.make_clusters(150, n_min=10, n_max=2048, rng=rng)
+    edge, eoff = synthetic.make_clusters(4, n_min=2048, n_max=2048, rng=rng)      # the largest fast size
+    over, ooff = synthetic.make_clusters(5, n_min=2049, n_max=5000, rng=rng)      # handed over
+    tiny, toff = synthetic.make_clusters(6, n_min=1, n_max=3, rng=rng)
+    parts, offs = [], [np.zeros(1, np.int64)]
+    for p_, o_ in ((pts, off), (over, ooff), (edge, eoff), (tiny, toff)):
+        parts.append(p_)
+        offs.append(o_[1:].astype(np.int64) + offs[-1][-1])
+    pts = np.concatenate(parts)
+    off = np.concatenate(offs).astype(np.int32)
+    V = 10
+    outs = {}
+    for variant in ("0", "1", "2", "3"):
+        monkeypatch.setenv("VG_PROJ_VARIANT", variant)
+        eng = Engine(num_views=V)
+        try:
+            outs[variant] = eng.project(pts, off, want_u8=True, want_densified=True)
+            again = eng.project(pts, off, want_u8=True)
+            assert torch.equal(outs[variant]["tiles"], again["tiles"])
+        finally:
+            eng.close()
+    ref = outs["0"]
+    st = ref["status"].cpu().numpy()
+    ok = st == 0                       # single-point clusters have no extent: flagged, taps not written
+    assert ok.sum() >= len(st) - 6
+    okt = torch.as_tensor(ok, device=ref["status"].device)
+    for variant in ("1", "2", "3"):
+        o = outs[variant]
+        assert torch.equal(o["status"], ref["status"]), variant
+        assert torch.equal(o["tiles"], ref["tiles"]), variant
+        assert torch.equal(o["u8"], ref["u8"]), variant
+        assert torch.equal(o["densified"].reshape(len(st), -1)[okt], ref["densified"].reshape(len(st), -1)[okt]), variant
+    sel = np.flatnonzero(ok)
+    sp = np.concatenate([pts[off[c]:off[c + 1]] for c in sel])
+    so = np.zeros(len(sel) + 1, np.int32)
+    so[1:] = np.cumsum([off[c + 1] - off[c] for c in sel])
+    dens_o, u8_o = opipe.project(sp, so, V, want_dens=True)
+    C = len(st)
+    assert np.array_equal(outs["1"]["densified"].cpu().numpy().reshape(C, V, 110, 110)[ok], dens_o)
+    assert np.array_equal(outs["1"]["u8"].cpu().numpy().reshape(C, V, 224, 224)[ok], u8_o)
+    assert torch.equal(tiles_to_u8(outs["1"]["tiles"]), outs["1"]["u8"])
+
+
 def test_r224_grid_against_reference_and_oracle(golden, engines):
     """BASELINE.json configs[3]: R = 224 grids (222x222 densified images).  Scatter winners bit-exact
     and densified <= 1e-5 against the reference's own run, every stage bit-exact against the oracle,

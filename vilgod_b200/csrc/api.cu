@@ -180,6 +180,8 @@ int vg_create(const VgConfig *cfg, VgHandle **out)
     }
     h->sw.ln_unfused = env_on("VG_LN_UNFUSED");
     h->sw.gemm_narrow = env_on("VG_GEMM_NARROW");
+    if (const char *pv = getenv("VG_PROJ_VARIANT"))
+        if (pv[0] >= '0' && pv[0] <= '3' && pv[1] == 0) h->sw.proj_variant = pv[0] - '0';
     if (env_on("VG_ATTN_TRACE") && cudaMalloc(&h->attn_trace, 16 * 8 * sizeof(long long)) != cudaSuccess)
         h->attn_trace = nullptr;
     *out = h;
@@ -194,6 +196,7 @@ void vg_destroy(VgHandle *h)
     if (h->proj_spill) cudaFree(h->proj_spill);
     if (h->proj_spill_flags) cudaFree(h->proj_spill_flags);
     if (h->proj_img_scratch) cudaFree(h->proj_img_scratch);
+    if (h->proj_defer) cudaFree(h->proj_defer);
     if (h->d_text) cudaFree(h->d_text);
     if (h->d_class_map) cudaFree(h->d_class_map);
     if (h->attn_trace) cudaFree(h->attn_trace);

@@ -111,10 +111,14 @@ struct VgHandle {
     void *proj_spill_flags = nullptr;
     void *proj_img_scratch = nullptr; // R = 224: per-SM running depth-max image (projection.cu)
     int proj_spill_sms = 0;
+    void *proj_defer = nullptr;     // hand-over list of the fast projection kernel (count + image indices)
+    bool proj_fast = false;         // R = 112 and an obj_ratio whose touched regions fit the fast kernel
     // A/B and debugging switches, read from the environment once in vg_create
     struct {
         bool ln_unfused = false;    // VG_LN_UNFUSED=1: separate LayerNorm kernels instead of the folded GEMMs
         bool gemm_narrow = false;   // VG_GEMM_NARROW=1: 4-warp / 4-stage residual epilogues everywhere
+        int proj_variant = 1;       // VG_PROJ_VARIANT: 0 = general kernel only, 1 = fast kernel (256 threads,
+                                    // 3 CTAs/SM, default), 2 = 256 x 2, 3 = 512 x 2
     } sw;
     long long *attn_trace = nullptr;   // VG_ATTN_TRACE: clock64 stamps of CTA 0 (attention_tcgen05.cu)
 };

@@ -37,6 +37,9 @@
 // the reference's order (explicit __f*_rn intrinsics: no FMA contraction), the bilinear stage uses
 // exactly the FMA pattern torch-CPU executes, the Gaussian uses a row-major FMA chain (the
 // reference's conv order is unspecified; 1e-5 contract).
+#include <algorithm>
+#include <cmath>
+
 #include "common.cuh"
 
 namespace vg {
@@ -83,6 +86,10 @@ struct ProjParams {
     int32_t *status;
     float *dbg_grid;
     float *dbg_dens;
+    // fast path hand-over: images the fast kernel does not take (more than FAST_N points, or a touched
+    // region beyond its shared-memory layout) are appended here and run by projection_kernel in list mode
+    int32_t *defer;        // [0] = count, [1 + i] = image index
+    int32_t block0;        // first image of this launch (fast kernel, launches above the list capacity)
 };
 
 template <int R> struct Geo {
@@ -344,15 +351,12 @@ __device__ __forceinline__ void gauss4(const float (&w)[9], const float (&ta)[6]
 }
 
 template <int R>
-__global__ void __launch_bounds__(NT, R == 112 ? 2 : 1) projection_kernel(const ProjParams P)
+__device__ __forceinline__ void project_image(const ProjParams &P, const int b, Smem<R> &sm)
 {
     using GE = Geo<R>;
     constexpr int Q = GE::Q, NS = GE::NS, MW = GE::MW;
     constexpr bool ISM = GE::kImgSmem;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem<R> &sm = *reinterpret_cast<Smem<R> *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.x;
     const int c = b / P.V, v = b - c * P.V;
     const int beg = P.offsets[c];
     const int n = P.offsets[c + 1] - beg;
@@ -960,14 +964,537 @@ __global__ void __launch_bounds__(NT, R == 112 ? 2 : 1) projection_kernel(const 
     }
 }
 
-template <int R>
+// one image per CTA, or -- list mode -- the images the fast kernel handed over, a fixed grid striding
+// over the list
+template <int R, bool LIST>
+__global__ void __launch_bounds__(NT, R == 112 ? 2 : 1) projection_kernel(const ProjParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem<R> &sm = *reinterpret_cast<Smem<R> *>(smem_raw);
+    if (!LIST) {
+        project_image<R>(P, (int)blockIdx.x, sm);
+        return;
+    }
+    const int count = P.defer[0];
+    for (int i = blockIdx.x; i < count; i += gridDim.x) {
+        project_image<R>(P, P.defer[1 + i], sm);
+        __syncthreads();       // the next image re-initialises the shared state
+    }
+}
+
+// =================================================================================================
+// Fast path: R = 112, clusters of up to FAST_N points (every cluster of a Waymo-shaped frame), images
+// whose touched region is at most F_MAXR rows x F_MAXS float4 strips (always, at the reference's
+// obj_ratio = 0.8: X, Y in [12, 101]).  Same arithmetic as project_image's stamp path -- the results
+// are bit-identical -- organised for instruction count:
+//   * 256-thread CTAs, ~63 KB of shared memory -> three CTAs per SM: half the per-warp replicated
+//     overhead of the 512-thread kernel, and three independent barrier domains per SM.
+//   * rotated points stay in registers between the min / max pass and the quantisation.
+//   * ONE bounding-box-limited buffer B (origin = the union of all slices' touched regions, fixed
+//     pitch, zero halo) holds the pooled slice; the running depth-max image lives in REGISTERS: a
+//     thread owns up to KQ (row pair, strip) items of the union for the whole image, so a slice costs
+//     no image load / store and no zero-initialisation pass, and a row pair shares two of its four
+//     pooled rows.  Neighbour columns arrive by shuffle (row starts / warp edges: one predicated load
+//     from the zero halo / the neighbouring warp's strip).
+//   * after the last slice the normalised image is written back into B (margins = 1.0) and the
+//     bilinear emit WALKS: a thread owns one 8-pixel column group and a run of output rows, keeps the
+//     horizontally interpolated source rows y0 / y0 + 1 in registers and advances them as the run
+//     moves down -- no intermediate buffer, no barrier, every horizontal interpolation done ~once.
+constexpr int FAST_N = 2048;
+constexpr int F_MAXR = 96, F_MAXS = 24;
+constexpr int F_PITCH = F_MAXS + 5;      // float4 strips per buffer row: two halo strips per side, odd
+constexpr int F_BROWS = F_MAXR + 3;      // halo row below / above + the second row of an odd last pair
+
+struct FastSmem {
+    float4 B[F_BROWS * F_PITCH];
+    uint2 cache[FAST_N];   // per point, sorted by depth slice: (x | y << 8, value bits)
+    unsigned ext[6];
+    unsigned rowmask[D][4], colmask[D][4];
+    int ylo[D], yhi[D], xlo[D], xhi[D], cnt[D], base[D];
+    int ulo, uhi, vlo, vhi;
+    int oy_lo, oy_hi, g_lo, g_hi;
+    float red[32];
+    int degenerate;
+    float2 lw[S];          // bilinear weights (l0, l1) of output row / column i ...
+    unsigned char i0[S];   // ... and its first source row / column (copy of ProjTables, filled per CTA)
+};
+
+template <int NTF, int MINB>
+__global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjParams P)
+{
+    constexpr int R = 112, Q = R - 2, NS = R / 4, MW = 4;
+    constexpr int NWF = NTF / 32;
+    constexpr int KP = (FAST_N + NTF - 1) / NTF;                        // points per thread
+    constexpr int KQ = ((F_MAXR / 2) * F_MAXS + NTF - 1) / NTF;         // (row pair, strip) items per thread
+    constexpr int PW = 4 * F_PITCH;                                     // buffer pitch in floats
+    static_assert(NTF >= S + NG && NTF >= 64, "setup roles are mapped to thread ids");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FastSmem &sm = *reinterpret_cast<FastSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = P.block0 + (int)blockIdx.x;
+    const int c = b / P.V, v = b - c * P.V;
+    const int beg = P.offsets[c];
+    const int n = P.offsets[c + 1] - beg;
+    auto hand_over = [&]() {
+        if (tid == 0) P.defer[1 + atomicAdd(P.defer, 1)] = b;
+    };
+    if (n > FAST_N) { hand_over(); return; }
+    const float *__restrict__ pts = P.points + 3 * (size_t)beg;
+    const float *rm = P.rot + 9 * v;
+    const bool fused = P.rotate_mode == VG_ROTATE_FUSED ||
+                       (P.rotate_mode == VG_ROTATE_TORCH_CPU && 9 * (long long)n >= 400);
+
+    // ---- phase 1: rotate (kept in registers), per-axis min / max ---------------------------------
+    float qx[KP], qy[KP], qz[KP];
+    {
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY;
+        float mn0 = INFINITY, mn1 = INFINITY, mn2 = INFINITY;
+        bool finite = true;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            const int i = tid + k * NTF;
+            if (i < n) {
+                rotate_point(pts + 3 * i, rm, fused, qx[k], qy[k], qz[k]);
+                finite = finite && isfinite(qx[k]) && isfinite(qy[k]) && isfinite(qz[k]);
+                mx0 = fmaxf(mx0, qx[k]); mx1 = fmaxf(mx1, qy[k]); mx2 = fmaxf(mx2, qz[k]);
+                mn0 = fminf(mn0, qx[k]); mn1 = fminf(mn1, qy[k]); mn2 = fminf(mn2, qz[k]);
+            }
+        }
+        if (tid < 6) sm.ext[tid] = tid < 3 ? 0u : 0xffffffffu;
+        if (tid < D * MW) { (&sm.rowmask[0][0])[tid] = 0u; (&sm.colmask[0][0])[tid] = 0u; }
+        if (tid < D) sm.cnt[tid] = 0;
+        if (tid < S) {
+            sm.lw[tid] = make_float2(__ldg(&P.tab->l0[tid]), __ldg(&P.tab->l1[tid]));
+            sm.i0[tid] = (unsigned char)__ldg(&P.tab->i0[tid]);
+        }
+        if (tid == 0) {
+            sm.degenerate = 0;
+            sm.ulo = Q; sm.uhi = -1; sm.vlo = Q; sm.vhi = -1;
+            sm.oy_lo = S; sm.oy_hi = -1; sm.g_lo = NG; sm.g_hi = -1;
+        }
+        const unsigned k0 = __reduce_max_sync(0xffffffffu, f2key(mx0));
+        const unsigned k1 = __reduce_max_sync(0xffffffffu, f2key(mx1));
+        const unsigned k2 = __reduce_max_sync(0xffffffffu, f2key(mx2));
+        const unsigned k3 = __reduce_min_sync(0xffffffffu, f2key(mn0));
+        const unsigned k4 = __reduce_min_sync(0xffffffffu, f2key(mn1));
+        const unsigned k5 = __reduce_min_sync(0xffffffffu, f2key(mn2));
+        const bool all_finite = __all_sync(0xffffffffu, finite);
+        __syncthreads();
+        if (lane == 0) {
+            atomicMax(&sm.ext[0], k0); atomicMax(&sm.ext[1], k1); atomicMax(&sm.ext[2], k2);
+            atomicMin(&sm.ext[3], k3); atomicMin(&sm.ext[4], k4); atomicMin(&sm.ext[5], k5);
+            if (!all_finite) sm.degenerate = 1;
+        }
+        __syncthreads();
+    }
+    Quant qn;
+    {
+        float a[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) a[k] = key2f(sm.ext[k]);
+        qn.cx = __fmul_rn(__fadd_rn(a[0], a[3]), 0.5f);
+        qn.cy = __fmul_rn(__fadd_rn(a[1], a[4]), 0.5f);
+        qn.cz = __fmul_rn(__fadd_rn(a[2], a[5]), 0.5f);
+        qn.pr = fmaxf(fmaxf(__fsub_rn(a[0], a[3]), __fsub_rn(a[1], a[4])), __fsub_rn(a[2], a[5]));
+    }
+    op_t *tile = P.tiles ? P.tiles + (size_t)b * VG_TILE_ELEMS : nullptr;
+    uint8_t *u8 = nullptr;
+    if (P.u8) {
+        if (!P.u8_first_only) u8 = P.u8 + (size_t)b * S * S;
+        else if (v == 0) u8 = P.u8 + (size_t)c * S * S;
+    }
+    if (sm.degenerate || n <= 0 || !(qn.pr > 0.0f) || !isfinite(qn.pr)) {
+        if (tile) {
+            uint4 *t = reinterpret_cast<uint4 *>(tile);
+            for (int i = tid; i < VG_TILE_ELEMS / 8; i += NTF) t[i] = make_uint4(0, 0, 0, 0);
+        }
+        if (u8) {
+            uint4 *t = reinterpret_cast<uint4 *>(u8);
+            for (int i = tid; i < S * S / 16; i += NTF) t[i] = make_uint4(0, 0, 0, 0);
+        }
+        if (P.status && v == 0 && tid == 0) P.status[c] = VG_EDEGENERATE;
+        return;
+    }
+    qn.rc_pr = __frcp_rn(qn.pr);
+    qn.rc_opb = __frcp_rn(P.one_plus_bias);
+    qn.slow = !(qn.pr > 1e-18f && qn.pr < 1e18f);
+
+    // ---- phase 2: quantise; per-slice counts and occupied rows / columns; counting sort by slice ----
+    uint2 *tmp = reinterpret_cast<uint2 *>(sm.B);      // unsorted (x | y << 8 | slice << 16 | rank << 19, value)
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        const int i = tid + k * NTF;
+        if (i < n) {
+            float val; int X, Y, zi;
+            quantise<R>(qx[k], qy[k], qz[k], qn, P, X, Y, zi, val);
+            atomicOr(&sm.rowmask[zi][Y >> 5], 1u << (Y & 31));
+            atomicOr(&sm.colmask[zi][X >> 5], 1u << (X & 31));
+            const unsigned rank = (unsigned)atomicAdd(&sm.cnt[zi], 1);
+            tmp[i] = make_uint2((unsigned)X | ((unsigned)Y << 8) | ((unsigned)zi << 16) | (rank << 19),
+                                __float_as_uint(val));
+        }
+    }
+    __syncthreads();
+    if (tid < 2 * D) {
+        const int d = tid >> 1;
+        const bool rows = (tid & 1) == 0;
+        int lo = R, hi = -1;
+#pragma unroll
+        for (int w = 0; w < MW; ++w) {
+            const unsigned bits = rows ? sm.rowmask[d][w] : sm.colmask[d][w];
+            if (bits) {
+                lo = min(lo, 32 * w + __ffs(bits) - 1);
+                hi = max(hi, 32 * w + 31 - __clz(bits));
+            }
+        }
+        if (rows) { sm.ylo[d] = lo; sm.yhi[d] = hi; } else { sm.xlo[d] = lo; sm.xhi[d] = hi; }
+        if (hi >= 0) {
+            atomicMin(rows ? &sm.ulo : &sm.vlo, max(lo - 4, 0));
+            atomicMax(rows ? &sm.uhi : &sm.vhi, min(hi + 2, Q - 1));
+        }
+    } else if (tid >= 32 && tid < 32 + D) {
+        int acc = 0;
+        for (int d = 0; d < tid - 32; ++d) acc += sm.cnt[d];
+        sm.base[tid - 32] = acc;
+    }
+    __syncthreads();
+    const int ulo = sm.ulo, uhi = sm.uhi, vlo = sm.vlo, vhi = sm.vhi;   // image cells any slice writes
+    const int nr = uhi - ulo + 1;
+    const int us_lo = vlo >> 2, ns = (vhi >> 2) - us_lo + 1;
+    const int npair = ((nr + 1) >> 1) * ns;
+    if (nr > F_MAXR || ns > F_MAXS || npair > KQ * NTF) { hand_over(); return; }    // block-uniform
+    if (P.status && v == 0 && tid == 0) P.status[c] = VG_OK;
+    const ProjTables *__restrict__ tab = P.tab;
+    if (tid < S) {
+        const int y0 = sm.i0[tid];
+        const int y1 = y0 + (y0 < Q - 1 ? 1 : 0);
+        if (!(y1 < ulo || y0 > uhi)) { atomicMin(&sm.oy_lo, tid); atomicMax(&sm.oy_hi, tid); }
+    } else if (tid < S + NG) {
+        const int g = tid - S;
+        const int xa = sm.i0[8 * g];
+        int xb = sm.i0[8 * g + 7];
+        xb += xb < Q - 1 ? 1 : 0;
+        if (!(xb < vlo || xa > vhi)) { atomicMin(&sm.g_lo, g); atomicMax(&sm.g_hi, g); }
+    }
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        const int i = tid + k * NTF;
+        if (i < n) {
+            const uint2 e = tmp[i];
+            sm.cache[sm.base[(e.x >> 16) & 7u] + (int)(e.x >> 19)] = make_uint2(e.x & 0xffffu, e.y);
+        }
+    }
+    __syncthreads();
+    const int oy_lo = sm.oy_lo, oy_hi = sm.oy_hi, g_lo = sm.g_lo, g_hi = sm.g_hi;
+    // buffer coordinates: grid row y -> y + orow, grid column x -> x + ocol (float index inside a row)
+    const int orow = 1 - ulo, ocol = 4 * (2 - us_lo);
+
+    // ---- background: every 16-byte piece of the tile outside the active rows x column groups is a copy
+    // of the precomputed background tile.  A warp owns the patch columns px = warp, warp + NWF, a lane the
+    // piece (row ky, half) of a patch, so the column test is loop invariant and a patch row costs one
+    // row test plus a load / store per owned patch ------------------------------------------------------
+    {
+        const int ky = lane >> 1, half = lane & 1;
+        constexpr int NPX = (14 + NWF - 1) / NWF;
+        bool colact[NPX];
+#pragma unroll
+        for (int j = 0; j < NPX; ++j) {
+            const int gg = 2 * (warp + j * NWF) + half;
+            colact[j] = gg >= g_lo && gg <= g_hi;
+        }
+        if (tile) {
+            const uint4 *__restrict__ src = tab->bg_tile + tid;
+            uint4 *dst = reinterpret_cast<uint4 *>(tile) + tid;
+#pragma unroll 7
+            for (int py = 0; py < 14; ++py) {
+                const int oy = 16 * py + ky;
+                const bool rowact = oy >= oy_lo && oy <= oy_hi;
+#pragma unroll
+                for (int j = 0; j < NPX; ++j)
+                    if (warp + j * NWF < 14 && !(rowact && colact[j]))
+                        dst[py * 448 + j * NTF] = __ldg(src + py * 448 + j * NTF);
+            }
+        }
+        if (u8) {
+            for (int py = 0; py < 14; ++py) {
+                const int oy = 16 * py + ky;
+                const bool rowact = oy >= oy_lo && oy <= oy_hi;
+#pragma unroll
+                for (int j = 0; j < NPX; ++j) {
+                    const int gg = 2 * (warp + j * NWF) + half;
+                    if (warp + j * NWF < 14 && !(rowact && colact[j]))
+                        *reinterpret_cast<uint2 *>(u8 + oy * S + 8 * gg) = __ldg(&tab->bg_u8[(oy * S + 8 * gg) >> 3]);
+                }
+            }
+        }
+    }
+
+    // ---- phase 3: per occupied slice: stamp the 5x5 footprints, 3x3 Gaussian, depth max ------------
+    // item k of a thread: rows (2 yp, 2 yp + 1) of the union x strip su; img0 / img1 = their running maxima
+    float4 img0[KQ], img1[KQ];
+    int boff[KQ];              // float index in B of the first row's strip; bit 29: take the left /
+                               // bit 30: the right neighbour column from memory instead of by shuffle
+#pragma unroll
+    for (int k = 0; k < KQ; ++k) {
+        const int item = tid + k * NTF;
+        const int yp = small_div(item, ns), su = item - yp * ns;
+        int o = ((2 * yp + 1) * F_PITCH + su + 2) * 4;
+        if (lane == 0 || su == 0) o |= 1 << 29;
+        if (lane == 31 || su == ns - 1) o |= 1 << 30;
+        boff[k] = o;
+        img0[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        img1[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float (&w)[9] = P.gauss;
+    unsigned occ = 0u;         // occupied depth slices
+#pragma unroll
+    for (int d = 0; d < D; ++d) occ |= sm.cnt[d] > 0 ? 1u << d : 0u;
+    bool first = true;
+    for (; occ; occ &= occ - 1) {
+        const int d = __ffs(occ) - 1;
+        const int cnt = sm.cnt[d];
+        if (!first) __syncthreads();       // every Gaussian read of the previous slice is done
+        first = false;
+        const int ylo = sm.ylo[d], yhi = sm.yhi[d], xlo = sm.xlo[d], xhi = sm.xhi[d];
+        if (lane < F_PITCH)
+            for (int r = warp; r < nr + 3; r += NWF) sm.B[r * F_PITCH + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+        {
+            // one item = one row of one point's 5x5 footprint (see project_image); all values are
+            // positive floats: integer order == float order
+            int *Bi = reinterpret_cast<int *>(sm.B) + orow * PW + ocol - 3 * PW - 3;
+            const uint2 *cache = sm.cache + sm.base[d];
+            if (xlo >= 3 && xhi <= Q - 2 && ylo >= 3 && yhi <= Q - 2) {      // no footprint leaves the image
+                for (int item = tid; item < 5 * cnt; item += NTF) {
+                    const int p = (item * 13108) >> 16, dy = item - 5 * p;     // item / 5 for item < 10,240
+                    const uint2 e = cache[p];
+                    int *row = Bi + ((int)(e.x >> 8) + dy) * PW + (int)(e.x & 255u);
+#pragma unroll
+                    for (int dx = 0; dx < 5; ++dx) atomicMax(row + dx, (int)e.y);
+                }
+            } else {
+                for (int item = tid; item < 5 * cnt; item += NTF) {
+                    const int p = (item * 13108) >> 16, dy = item - 5 * p;
+                    const uint2 e = cache[p];
+                    const int X = (int)(e.x & 255u), Y = (int)(e.x >> 8);
+                    const int q = Y - 3 + dy;
+                    if (q < 0 || q > Q - 1) continue;
+                    int *row = Bi + (Y + dy) * PW + X;
+#pragma unroll
+                    for (int dx = 0; dx < 5; ++dx) {
+                        const int x = X - 3 + dx;
+                        if (x >= 0 && x <= Q - 1) atomicMax(row + dx, (int)e.y);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        {
+            // smoothed rows of this slice: [gy0, gy1]; a pair takes part when one of its rows is inside
+            const int gy0 = max(ylo - 4, 0), gy1 = min(yhi + 2, Q - 1);
+            const unsigned lo = (unsigned)((gy0 + orow - 1) * PW), span = (unsigned)((gy1 - gy0 + 2) * PW);
+            const float *Bf = reinterpret_cast<const float *>(sm.B);
+#pragma unroll
+            for (int k = 0; k < KQ; ++k) {
+                if (k * NTF + (tid & ~31) >= npair) break;                 // warp-uniform
+                const int o = boff[k] & 0x1fffffff;
+                const bool act = tid + k * NTF < npair && (unsigned)(o - (int)lo) < span;
+                if (!__any_sync(0xffffffffu, act)) continue;
+                const float *cen = Bf + (act ? o : 4 * F_PITCH + 8);      // inactive lanes read a valid cell
+                const bool ml = (boff[k] >> 29) & 1, mr = (boff[k] >> 30) & 1;
+                float t[4][6];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float *row = cen + (r - 1) * PW;
+                    const float4 cc = *reinterpret_cast<const float4 *>(row);
+                    float l = __shfl_up_sync(0xffffffffu, cc.w, 1);
+                    float rr = __shfl_down_sync(0xffffffffu, cc.x, 1);
+                    if (ml) l = row[-1];
+                    if (mr) rr = row[4];
+                    t[r][0] = l; t[r][1] = cc.x; t[r][2] = cc.y; t[r][3] = cc.z; t[r][4] = cc.w; t[r][5] = rr;
+                }
+                float o0[4], o1[4];
+                gauss4(w, t[0], t[1], t[2], o0);
+                gauss4(w, t[1], t[2], t[3], o1);
+                if (act) {
+                    img0[k] = max4(img0[k], make_float4(o0[0], o0[1], o0[2], o0[3]));
+                    img1[k] = max4(img1[k], make_float4(o1[0], o1[1], o1[2], o1[3]));
+                }
+            }
+        }
+    }
+
+    // ---- phase 4: img / max(img), 1 - x; the normalised image goes back into B, margins = 1.0 ------
+    {
+        float m = 0.0f;
+#pragma unroll
+        for (int k = 0; k < KQ; ++k) {
+            const int item = tid + k * NTF;
+            if (item >= npair) {
+                img0[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                img1[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                continue;
+            }
+            const int o = (boff[k] & 0x1fffffff) >> 2;
+            const int rb = o / F_PITCH, sb = o - rb * F_PITCH;            // buffer row (first of the pair), strip
+            if (rb + 1 > nr) img1[k] = make_float4(0.f, 0.f, 0.f, 0.f);   // second row of an odd last pair
+            if (sb - 2 + us_lo == NS - 1) {                               // columns Q, Q + 1 are padding
+                img0[k].z = 0.0f; img0[k].w = 0.0f;
+                img1[k].z = 0.0f; img1[k].w = 0.0f;
+            }
+            m = fmaxf(fmaxf(m, fmaxf(img0[k].x, img0[k].y)), fmaxf(img0[k].z, img0[k].w));
+            m = fmaxf(fmaxf(m, fmaxf(img1[k].x, img1[k].y)), fmaxf(img1[k].z, img1[k].w));
+        }
+        m = warp_max(m);
+        if (lane == 0) sm.red[warp] = m;
+        __syncthreads();                   // also: every Gaussian read of the last slice is done
+        float mx = sm.red[0];
+#pragma unroll
+        for (int i = 1; i < NWF; ++i) mx = fmaxf(mx, sm.red[i]);
+        const float rc_mx = __frcp_rn(mx);
+        auto norm4 = [&](float4 t) {
+            t.x = __fsub_rn(1.0f, div_rn(t.x, mx, rc_mx, false));
+            t.y = __fsub_rn(1.0f, div_rn(t.y, mx, rc_mx, false));
+            t.z = __fsub_rn(1.0f, div_rn(t.z, mx, rc_mx, false));
+            t.w = __fsub_rn(1.0f, div_rn(t.w, mx, rc_mx, false));
+            return t;
+        };
+        const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (lane < F_PITCH) {
+            const bool edge = lane < 2 || lane >= ns + 2;
+            for (int rb = warp; rb < nr + 3; rb += NWF)
+                if (edge || rb == 0 || rb > nr) sm.B[rb * F_PITCH + lane] = one4;
+        }
+#pragma unroll
+        for (int k = 0; k < KQ; ++k) {
+            if (tid + k * NTF < npair) {
+                const int o = (boff[k] & 0x1fffffff) >> 2;
+                sm.B[o] = norm4(img0[k]);
+                if (o / F_PITCH + 1 <= nr) sm.B[o + F_PITCH] = norm4(img1[k]);
+            }
+        }
+        __syncthreads();
+        if (P.dbg_dens) {
+            float *dd = P.dbg_dens + (size_t)b * Q * Q;
+            const float *Bf = reinterpret_cast<const float *>(sm.B);
+            for (int i = tid; i < Q * Q; i += NTF) {
+                const int y = i / Q, x = i - y * Q;
+                const int rb = y + orow, cb = x + ocol;
+                const bool in = rb >= 0 && rb <= nr + 1 && cb >= 0 && cb < 4 * (ns + 4);
+                dd[i] = in ? Bf[rb * PW + cb] : 1.0f;
+            }
+        }
+    }
+
+    // ---- phase 5: bilinear Q -> 224 (align_corners), floor(x*255), patch-major tiles ---------------
+    // out = fma(HI[y0], lh0, HI[y0 + 1] * lh1), HI[y][ox] = fma(B[y][x0], lw0, B[y][x0 + 1] * lw1): the
+    // contraction pattern of torch-CPU's separable interpolation.  (At the last source row / column the
+    // reference clamps the second index; its weight is exactly 0 there and B holds a finite value one
+    // step further, so the unclamped read gives the same +0 product.)
+    if (oy_hi < oy_lo || g_hi < g_lo) return;
+    {
+        const int ng = g_hi - g_lo + 1;
+        const int nseg = small_div(NTF, ng);
+        const int seg = small_div(tid, ng);
+        if (seg >= nseg) return;
+        const int g = g_lo + (tid - seg * ng);
+        // a thread owns column group g and a run of SOURCE rows [ys, ye]: per source row one horizontal
+        // interpolation (the row below is carried over) and the two or three output rows whose upper
+        // source row it is
+        const int ya = sm.i0[oy_lo], yb = sm.i0[oy_hi];
+        const int len = small_div(yb - ya + nseg, nseg);
+        const int ys = ya + seg * len, ye = min(ys + len - 1, yb);
+        if (ys > ye) return;
+        int oy = min((ys * (S - 1)) / (Q - 1), S - 1);                  // close to the first row with y0 == ys
+        while (oy > oy_lo && (int)sm.i0[oy - 1] >= ys) --oy;
+        while ((int)sm.i0[oy] < ys) ++oy;                                // i0 reaches yb >= ys at oy_hi
+        oy = max(oy, oy_lo);
+        const float *Bf = reinterpret_cast<const float *>(sm.B) + orow * PW + ocol;
+        int xo[8];
+        float lw0[8], lw1[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            xo[j] = sm.i0[8 * g + j];
+            const float2 t = sm.lw[8 * g + j];
+            lw0[j] = t.x; lw1[j] = t.y;
+        }
+        float ha[8], hb[8];
+        auto hrow = [&](int y, float (&h)[8]) {
+            const float *row = Bf + y * PW;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                h[j] = __fmaf_rn(row[xo[j]], lw0[j], __fmul_rn(row[xo[j] + 1], lw1[j]));
+        };
+        const f32x2 k255 = pack2(255.0f, 255.0f), kmagic = pack2(8388608.0f, 8388608.0f);
+        op_t *tdst = tile ? tile + (g >> 1) * 256 + (g & 1) * 8 : nullptr;
+        hrow(ys, hb);
+        for (int y = ys; y <= ye; ++y) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ha[j] = hb[j];
+            hrow(y + 1, hb);
+            while (oy <= oy_hi && (int)sm.i0[oy] == y) {
+                const float2 lh = sm.lw[oy];
+                const f32x2 h0 = pack2(lh.x, lh.x), h1 = pack2(lh.y, lh.y);
+                unsigned fb[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const f32x2 o = fma2(pack2(ha[2 * j], ha[2 * j + 1]), h0, mul2(pack2(hb[2 * j], hb[2 * j + 1]), h1));
+                    const f32x2 q = sub2(add2_rz(mul2(o, k255), kmagic), kmagic);
+                    float q0, q1;
+                    unpack2(q, q0, q1);
+                    fb[2 * j] = __float_as_uint(q0);
+                    fb[2 * j + 1] = __float_as_uint(q1);
+                }
+                if (tdst) {
+                    uint4 pk;
+#ifndef VG_OPERAND_BF16
+                    pk.x = pack_op(__uint_as_float(fb[0]), __uint_as_float(fb[1]));
+                    pk.y = pack_op(__uint_as_float(fb[2]), __uint_as_float(fb[3]));
+                    pk.z = pack_op(__uint_as_float(fb[4]), __uint_as_float(fb[5]));
+                    pk.w = pack_op(__uint_as_float(fb[6]), __uint_as_float(fb[7]));
+#else
+                    pk.x = __byte_perm(fb[0], fb[1], 0x7632);
+                    pk.y = __byte_perm(fb[2], fb[3], 0x7632);
+                    pk.z = __byte_perm(fb[4], fb[5], 0x7632);
+                    pk.w = __byte_perm(fb[6], fb[7], 0x7632);
+#endif
+                    *reinterpret_cast<uint4 *>(tdst + (oy >> 4) * (14 * 256) + (oy & 15) * 16) = pk;
+                }
+                if (u8) {
+                    unsigned lo = 0, hi = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        lo |= ((unsigned)__uint_as_float(fb[j])) << (8 * j);
+                        hi |= ((unsigned)__uint_as_float(fb[4 + j])) << (8 * j);
+                    }
+                    *reinterpret_cast<uint2 *>(u8 + oy * S + 8 * g) = make_uint2(lo, hi);
+                }
+                ++oy;
+            }
+        }
+    }
+}
+
+template <int R, bool LIST>
 int launch_projection_t(VgHandle *h, const ProjParams &P, long long blocks, cudaStream_t st)
 {
-    int rc = vg_set_smem_once(h, reinterpret_cast<const void *>(projection_kernel<R>), sizeof(Smem<R>));
+    int rc = vg_set_smem_once(h, reinterpret_cast<const void *>(projection_kernel<R, LIST>), sizeof(Smem<R>));
     if (rc) return rc;
-    projection_kernel<R><<<(unsigned)blocks, NT, sizeof(Smem<R>), st>>>(P);
+    projection_kernel<R, LIST><<<(unsigned)blocks, NT, sizeof(Smem<R>), st>>>(P);
     return VG_OK;
 }
+
+template <int NTF, int MINB>
+int launch_fast_t(VgHandle *h, const ProjParams &P, long long blocks, cudaStream_t st)
+{
+    int rc = vg_set_smem_once(h, reinterpret_cast<const void *>(projection_fast_kernel<NTF, MINB>),
+                              sizeof(FastSmem));
+    if (rc) return rc;
+    projection_fast_kernel<NTF, MINB><<<(unsigned)blocks, NTF, sizeof(FastSmem), st>>>(P);
+    return VG_OK;
+}
+
+constexpr long long kDeferCap = 1ll << 20;     // images per fast launch (capacity of the hand-over list)
 
 }  // namespace
 
@@ -991,6 +1518,20 @@ int projection_init(VgHandle *h)
     VG_CUDA_CHECK(h, cudaMemset(h->proj_spill_flags, 0, slots * sizeof(int)));
     if (R == 224)    // running depth-max image of the one CTA resident on each SM (~29 MB)
         VG_CUDA_CHECK(h, cudaMalloc(&h->proj_img_scratch, (size_t)nsmid * Q * R * sizeof(float)));
+    // hand-over list of the fast kernel (count + image indices, 4 MB)
+    VG_CUDA_CHECK(h, cudaMalloc(&h->proj_defer, (size_t)(kDeferCap + 1) * sizeof(int32_t)));
+    // The fast kernel's shared-memory layout covers touched regions of F_MAXR rows x F_MAXS strips.
+    // X, Y = clip(ceil(((u * obj_ratio + 1) / 2) * R), 1, R - 2) with |u| <= 1 up to a few ulps (1e-3 of
+    // a cell covers them); the touched region adds 4 cells below and 2 above.  The kernel checks every
+    // image against its layout anyway and hands over what does not fit.
+    {
+        const double rho = h->cfg.obj_ratio;
+        const int lo = (int)std::max(1.0, std::ceil((1.0 - rho) * 0.5 * R - 1e-3));
+        const int hi = (int)std::min((double)(R - 2), std::ceil((1.0 + rho) * 0.5 * R + 1e-3));
+        const int rows = std::min(hi + 2, Q - 1) - std::max(lo - 4, 0) + 1;
+        const int strips = (std::min(hi + 2, Q - 1) >> 2) - (std::max(lo - 4, 0) >> 2) + 1;
+        h->proj_fast = R == 112 && rows <= F_MAXR && strips <= F_MAXS;
+    }
     VG_CUDA_CHECK(h, cudaDeviceSynchronize());
     return VG_OK;
 }
@@ -1029,11 +1570,33 @@ int launch_projection(VgHandle *h, const float *d_points, const int32_t *d_offse
     P.status = d_status;
     P.dbg_grid = dbg ? dbg->d_grid : nullptr;
     P.dbg_dens = dbg ? dbg->d_densified : nullptr;
+    P.defer = static_cast<int32_t *>(h->proj_defer);
+    P.block0 = 0;
     const long long blocks = (long long)C * cfg.num_views;
     // algorithmic bytes recorded here: the emitted tiles; the caller adds 12 * sum(N) for the points
     VgProfScope prof(h, VG_K_PROJECTION, (double)blocks * VG_TILE_ELEMS * 2.0, st);
-    int rc = cfg.resolution == 112 ? launch_projection_t<112>(h, P, blocks, st)
-                                   : launch_projection_t<224>(h, P, blocks, st);
+    int rc;
+    if (h->proj_fast && h->sw.proj_variant != 0 && !P.dbg_grid) {
+        // fast kernel over every image; what it hands over (clusters above FAST_N points) runs in the
+        // general kernel in list mode, two CTAs per SM striding over the list
+        for (long long b0 = 0; b0 < blocks; b0 += kDeferCap) {
+            const long long nb = std::min(kDeferCap, blocks - b0);
+            VG_CUDA_CHECK(h, cudaMemsetAsync(P.defer, 0, sizeof(int32_t), st));
+            P.block0 = (int32_t)b0;
+            switch (h->sw.proj_variant) {
+            case 2: rc = launch_fast_t<256, 2>(h, P, nb, st); break;
+            case 3: rc = launch_fast_t<512, 2>(h, P, nb, st); break;
+            default: rc = launch_fast_t<256, 3>(h, P, nb, st); break;
+            }
+            if (rc) return rc;
+            VG_LAUNCH_CHECK(h);
+            if ((rc = launch_projection_t<112, true>(h, P, std::min<long long>(nb, 2ll * h->num_sms), st))) return rc;
+            VG_LAUNCH_CHECK(h);
+        }
+        return VG_OK;
+    }
+    rc = cfg.resolution == 112 ? launch_projection_t<112, false>(h, P, blocks, st)
+                               : launch_projection_t<224, false>(h, P, blocks, st);
     if (rc) return rc;
     VG_LAUNCH_CHECK(h);
     return VG_OK;
