@@ -11,6 +11,11 @@ using namespace vg;
 namespace {
 
 constexpr int64_t kMaxChunkImages = 4096;
+// vg_classify projects up to this many images back to back before the tower runs over them in
+// chunks (26 GB of tiles at most): the projection is instruction bound, and between the tower's GEMMs
+// it would run at the SM clock the 1000 W cap leaves them (~1.1 GHz); on its own for a few
+// milliseconds the board clocks it up.  VG_PROJ_BATCH (images) overrides, e.g. 4096 = one chunk.
+constexpr int64_t kMaxProjImages = 262144;
 // per image: residual stream fp32 + one bf16 [197,768] buffer + one bf16 [197,3072] buffer
 constexpr size_t kEncodeBytesPerImage =
     (size_t)kTokens * ((size_t)kWidth * 4 + (size_t)kWidth * 2 + (size_t)kMlp * 2);
@@ -180,6 +185,11 @@ int vg_create(const VgConfig *cfg, VgHandle **out)
     }
     h->sw.ln_unfused = env_on("VG_LN_UNFUSED");
     h->sw.gemm_narrow = env_on("VG_GEMM_NARROW");
+    h->proj_batch_images = kMaxProjImages;
+    if (const char *pb = getenv("VG_PROJ_BATCH")) {
+        const long long v = atoll(pb);
+        if (v >= 1) h->proj_batch_images = v < kMaxProjImages ? v : kMaxProjImages;
+    }
     if (const char *pv = getenv("VG_PROJ_VARIANT"))
         if (pv[0] >= '0' && pv[0] <= '3' && pv[1] == 0) h->sw.proj_variant = pv[0] - '0';
     if (env_on("VG_ATTN_TRACE") && cudaMalloc(&h->attn_trace, 16 * 8 * sizeof(long long)) != cudaSuccess)
@@ -282,7 +292,9 @@ size_t vg_workspace_bytes(const VgHandle *h, int64_t max_images)
 {
     if (!h || max_images <= 0) return 0;
     const int64_t chunk = max_images < kMaxChunkImages ? max_images : kMaxChunkImages;
-    return encode_bytes(chunk) + align_up((size_t)chunk * kTileBytesPerImage, 1024) + 4096;
+    int64_t batch = max_images < h->proj_batch_images ? max_images : h->proj_batch_images;
+    if (batch < chunk) batch = chunk;
+    return encode_bytes(chunk) + align_up((size_t)batch * kTileBytesPerImage, 1024) + 4096;
 }
 
 int vg_canonicalise(VgHandle *h, const float *d_points_in, const int32_t *d_offsets, int32_t C,
@@ -375,7 +387,7 @@ int vg_classify(VgHandle *h, const float *d_points, const int32_t *d_offsets, in
     if (cc > C) cc = C;
     if (cc < 1) cc = 1;
     auto need = [&](int64_t c) {
-        return align_up((size_t)c * V * kTileBytesPerImage, 1024) + encode_bytes(c * V);
+        return align_up(encode_bytes(c * V), 1024) + (size_t)c * V * kTileBytesPerImage;
     };
     while (cc > 1 && need(cc) > ws_bytes) cc = (cc + 1) / 2;
     if (need(cc) > ws_bytes) {
@@ -383,19 +395,30 @@ int vg_classify(VgHandle *h, const float *d_points, const int32_t *d_offsets, in
                    ws_bytes, need(cc), (long long)cc);
         return VG_EWORKSPACE;
     }
-    op_t *tiles = static_cast<op_t *>(d_ws);
-    char *enc_ws = static_cast<char *>(d_ws) + align_up((size_t)cc * V * kTileBytesPerImage, 1024);
+    // projection batch: as many chunks of tiles as the rest of the workspace holds (at least one)
+    const size_t enc_bytes = align_up(encode_bytes(cc * V), 1024);
+    int64_t pb = (int64_t)((ws_bytes - enc_bytes) / ((size_t)V * kTileBytesPerImage));
+    if (pb > h->proj_batch_images / V) pb = h->proj_batch_images / V;
+    if (pb >= C) pb = C;
+    else pb = pb / cc * cc;            // whole chunks
+    if (pb < cc) pb = cc;
+    char *enc_ws = static_cast<char *>(d_ws);
+    op_t *tiles = reinterpret_cast<op_t *>(enc_ws + enc_bytes);
     const EncodeBuffers eb = carve(enc_ws, cc * V);
     const int P = h->num_prompts;
-    for (int64_t c0 = 0; c0 < C; c0 += cc) {
-        const int64_t n = C - c0 < cc ? C - c0 : cc;
-        int rc = launch_projection(h, d_points, d_offsets + c0, (int32_t)n, tiles,
-                                   d_u8_first ? d_u8_first + (size_t)c0 * 224 * 224 : nullptr, true,
-                                   d_status ? d_status + c0 : nullptr, nullptr, st);
+    for (int64_t p0 = 0; p0 < C; p0 += pb) {
+        const int64_t np = C - p0 < pb ? C - p0 : pb;
+        int rc = launch_projection(h, d_points, d_offsets + p0, (int32_t)np, tiles,
+                                   d_u8_first ? d_u8_first + (size_t)p0 * 224 * 224 : nullptr, true,
+                                   d_status ? d_status + p0 : nullptr, nullptr, st);
         if (rc) return rc;
-        rc = encode_chunk(h, tiles, n * V, eb, d_probs + c0 * V * P, d_top1 + c0 * V,
-                          d_feats ? d_feats + c0 * V * kEmbed : nullptr, nullptr, nullptr, st);
-        if (rc) return rc;
+        for (int64_t c0 = p0; c0 < p0 + np; c0 += cc) {
+            const int64_t n = p0 + np - c0 < cc ? p0 + np - c0 : cc;
+            rc = encode_chunk(h, tiles + (size_t)(c0 - p0) * V * VG_TILE_ELEMS, n * V, eb,
+                              d_probs + c0 * V * P, d_top1 + c0 * V,
+                              d_feats ? d_feats + c0 * V * kEmbed : nullptr, nullptr, nullptr, st);
+            if (rc) return rc;
+        }
     }
     if (d_voted_class && d_voted_score)
         return launch_vote(h, d_probs, d_top1, C, d_voted_class, d_voted_score, st);

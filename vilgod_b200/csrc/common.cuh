@@ -112,6 +112,7 @@ struct VgHandle {
     void *proj_img_scratch = nullptr; // R = 224: per-SM running depth-max image (projection.cu)
     int proj_spill_sms = 0;
     void *proj_defer = nullptr;     // hand-over list of the fast projection kernel (count + image indices)
+    int64_t proj_batch_images = 0;  // images vg_classify projects back to back before the tower (api.cu)
     bool proj_fast = false;         // R = 112 and an obj_ratio whose touched regions fit the fast kernel
     // A/B and debugging switches, read from the environment once in vg_create
     struct {

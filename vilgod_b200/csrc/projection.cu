@@ -1428,12 +1428,14 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
         const f32x2 k255 = pack2(255.0f, 255.0f), kmagic = pack2(8388608.0f, 8388608.0f);
         op_t *tdst = tile ? tile + (g >> 1) * 256 + (g & 1) * 8 : nullptr;
         hrow(ys, hb);
+        int ynext = sm.i0[oy];             // upper source row of output row oy, loaded one row ahead
         for (int y = ys; y <= ye; ++y) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) ha[j] = hb[j];
             hrow(y + 1, hb);
-            while (oy <= oy_hi && (int)sm.i0[oy] == y) {
+            while (oy <= oy_hi && ynext == y) {
                 const float2 lh = sm.lw[oy];
+                ynext = sm.i0[min(oy + 1, S - 1)];
                 const f32x2 h0 = pack2(lh.x, lh.x), h1 = pack2(lh.y, lh.y);
                 unsigned fb[8];
 #pragma unroll
