@@ -113,6 +113,8 @@ def load(operand_dtype="f16"):
         raise ValueError(f"operand_dtype must be one of {sorted(LIB_PATHS)}")
     if operand_dtype not in _libs:
         path = LIB_PATHS[operand_dtype]
+        if operand_dtype == "f16" and os.environ.get("VG_LIB_PATH"):
+            path = os.environ["VG_LIB_PATH"]      # instrumented debug build (python -m vilgod_b200.build --trace)
         if not os.path.exists(path):
             raise RuntimeError(
                 f"{path} not built: run `python -m vilgod_b200.build` (needs nvcc, sm_100a). "

@@ -31,17 +31,21 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False, bf16=False):
+LIB_PATH_TRACE = os.path.join(OUT_DIR, "libvilgod_b200_trace.so")  # debug: -DVG_PROJ_TRACE (load with VG_LIB_PATH)
+
+
+def build_library(force=False, verbose=False, bf16=False, trace=False):
     os.makedirs(OUT_DIR, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
     objs, jobs = [], []
-    lib_path = LIB_PATH_BF16 if bf16 else LIB_PATH
+    lib_path = LIB_PATH_TRACE if trace else LIB_PATH_BF16 if bf16 else LIB_PATH
     for s in SOURCES:
         src = os.path.join(CSRC, s)
-        obj = os.path.join(OUT_DIR, s.replace(".cu", "_bf16.o" if bf16 else ".o"))
+        obj = os.path.join(OUT_DIR, s.replace(".cu", "_trace.o" if trace else "_bf16.o" if bf16 else ".o"))
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs):
             cmd = ([_nvcc()] + NVCC_FLAGS + (["-DVG_OPERAND_BF16=1"] if bf16 else [])
+                   + (["-DVG_PROJ_TRACE=1"] if trace else [])
                    + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj])
             jobs.append(cmd)
 
@@ -66,4 +70,7 @@ def build_all(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build_all(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--trace" in sys.argv:
+        print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, trace=True))
+    else:
+        print(build_all(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -207,6 +207,7 @@ void vg_destroy(VgHandle *h)
     if (h->proj_spill_flags) cudaFree(h->proj_spill_flags);
     if (h->proj_img_scratch) cudaFree(h->proj_img_scratch);
     if (h->proj_defer) cudaFree(h->proj_defer);
+    if (h->proj_trace) cudaFree(h->proj_trace);
     if (h->d_text) cudaFree(h->d_text);
     if (h->d_class_map) cudaFree(h->d_class_map);
     if (h->attn_trace) cudaFree(h->attn_trace);

@@ -113,6 +113,9 @@ struct VgHandle {
     int proj_spill_sms = 0;
     void *proj_defer = nullptr;     // hand-over list of the fast projection kernel (count + image indices)
     int64_t proj_batch_images = 0;  // images vg_classify projects back to back before the tower (api.cu)
+    long long *proj_trace = nullptr; // VG_PROJ_TRACE: per-image phase stamps of the fast projection kernel
+    uint32_t proj_bg_splat = 0, proj_bg_u8_splat = 0;   // constant background (two operand pixels / four bytes)
+    bool proj_table_exact = false;  // bilinear source index table == floor(o (Q-1) / (S-1))
     bool proj_fast = false;         // R = 112 and an obj_ratio whose touched regions fit the fast kernel
     // A/B and debugging switches, read from the environment once in vg_create
     struct {

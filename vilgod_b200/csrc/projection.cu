@@ -90,7 +90,12 @@ struct ProjParams {
     // region beyond its shared-memory layout) are appended here and run by projection_kernel in list mode
     int32_t *defer;        // [0] = count, [1 + i] = image index
     int32_t block0;        // first image of this launch (fast kernel, launches above the list capacity)
+    long long *trace;      // VG_PROJ_TRACE: clock64 stamps of thread 0 at the phase boundaries, [image][12]
+    uint32_t bg_splat;     // two operand-typed background pixels when the whole background tile is one value
+                           // (R = 112: 255 everywhere), else 0: copy the tile from memory
+    uint32_t bg_u8_splat;  // likewise four uint8 background pixels, valid when bg_splat != 0
 };
+constexpr int kTraceImages = 32768;
 
 template <int R> struct Geo {
     static constexpr int Q = R - 2;             // densified image size (110 / 222)
@@ -1012,12 +1017,24 @@ struct FastSmem {
     unsigned rowmask[D][4], colmask[D][4];
     int ylo[D], yhi[D], xlo[D], xhi[D], cnt[D], base[D];
     int ulo, uhi, vlo, vhi;
-    int oy_lo, oy_hi, g_lo, g_hi;
     float red[32];
     int degenerate;
     float2 lw[S];          // bilinear weights (l0, l1) of output row / column i ...
     unsigned char i0[S];   // ... and its first source row / column (copy of ProjTables, filled per CTA)
 };
+
+// phase timeline of the fast kernel: compiled in only with -DVG_PROJ_TRACE (python -m vilgod_b200.build
+// --trace -> libvilgod_b200_trace.so); the counters would otherwise cost registers in the slice loop
+#ifdef VG_PROJ_TRACE
+#define VG_TR(k)                                                                   \
+    do {                                                                           \
+        if (P.trace && tid == 0 && b < kTraceImages) P.trace[b * 12 + (k)] = clock64(); \
+    } while (0)
+#define VG_TR_ON(x) x
+#else
+#define VG_TR(k) do { } while (0)
+#define VG_TR_ON(x)
+#endif
 
 template <int NTF, int MINB>
 __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjParams P)
@@ -1027,18 +1044,36 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
     constexpr int KP = (FAST_N + NTF - 1) / NTF;                        // points per thread
     constexpr int KQ = ((F_MAXR / 2) * F_MAXS + NTF - 1) / NTF;         // (row pair, strip) items per thread
     constexpr int PW = 4 * F_PITCH;                                     // buffer pitch in floats
-    static_assert(NTF >= S + NG && NTF >= 64, "setup roles are mapped to thread ids");
+    static_assert(NTF >= S && NTF >= 64, "setup roles are mapped to thread ids");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FastSmem &sm = *reinterpret_cast<FastSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = P.block0 + (int)blockIdx.x;
     const int c = b / P.V, v = b - c * P.V;
+    // shared state first, and ONE early barrier (every warp reaches it at once) instead of one between
+    // the reduction's initial values and its atomics; the bilinear table is requested now and stored
+    // once the points are through
+    float2 t_lw = make_float2(0.f, 0.f);
+    int t_i0 = 0;
+    if (tid < S) {
+        t_lw = make_float2(__ldg(&P.tab->l0[tid]), __ldg(&P.tab->l1[tid]));
+        t_i0 = __ldg(&P.tab->i0[tid]);
+    }
+    if (tid < 6) sm.ext[tid] = tid < 3 ? 0u : 0xffffffffu;
+    if (tid < D * MW) { (&sm.rowmask[0][0])[tid] = 0u; (&sm.colmask[0][0])[tid] = 0u; }
+    if (tid < D) sm.cnt[tid] = 0;
+    if (tid == 0) {
+        sm.degenerate = 0;
+        sm.ulo = Q; sm.uhi = -1; sm.vlo = Q; sm.vhi = -1;
+    }
     const int beg = P.offsets[c];
     const int n = P.offsets[c + 1] - beg;
     auto hand_over = [&]() {
         if (tid == 0) P.defer[1 + atomicAdd(P.defer, 1)] = b;
     };
     if (n > FAST_N) { hand_over(); return; }
+    VG_TR(0);
+    __syncthreads();
     const float *__restrict__ pts = P.points + 3 * (size_t)beg;
     const float *rm = P.rot + 9 * v;
     const bool fused = P.rotate_mode == VG_ROTATE_FUSED ||
@@ -1060,18 +1095,6 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
                 mn0 = fminf(mn0, qx[k]); mn1 = fminf(mn1, qy[k]); mn2 = fminf(mn2, qz[k]);
             }
         }
-        if (tid < 6) sm.ext[tid] = tid < 3 ? 0u : 0xffffffffu;
-        if (tid < D * MW) { (&sm.rowmask[0][0])[tid] = 0u; (&sm.colmask[0][0])[tid] = 0u; }
-        if (tid < D) sm.cnt[tid] = 0;
-        if (tid < S) {
-            sm.lw[tid] = make_float2(__ldg(&P.tab->l0[tid]), __ldg(&P.tab->l1[tid]));
-            sm.i0[tid] = (unsigned char)__ldg(&P.tab->i0[tid]);
-        }
-        if (tid == 0) {
-            sm.degenerate = 0;
-            sm.ulo = Q; sm.uhi = -1; sm.vlo = Q; sm.vhi = -1;
-            sm.oy_lo = S; sm.oy_hi = -1; sm.g_lo = NG; sm.g_hi = -1;
-        }
         const unsigned k0 = __reduce_max_sync(0xffffffffu, f2key(mx0));
         const unsigned k1 = __reduce_max_sync(0xffffffffu, f2key(mx1));
         const unsigned k2 = __reduce_max_sync(0xffffffffu, f2key(mx2));
@@ -1079,11 +1102,14 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
         const unsigned k4 = __reduce_min_sync(0xffffffffu, f2key(mn1));
         const unsigned k5 = __reduce_min_sync(0xffffffffu, f2key(mn2));
         const bool all_finite = __all_sync(0xffffffffu, finite);
-        __syncthreads();
         if (lane == 0) {
             atomicMax(&sm.ext[0], k0); atomicMax(&sm.ext[1], k1); atomicMax(&sm.ext[2], k2);
             atomicMin(&sm.ext[3], k3); atomicMin(&sm.ext[4], k4); atomicMin(&sm.ext[5], k5);
             if (!all_finite) sm.degenerate = 1;
+        }
+        if (tid < S) {
+            sm.lw[tid] = t_lw;
+            sm.i0[tid] = (unsigned char)t_i0;
         }
         __syncthreads();
     }
@@ -1118,6 +1144,7 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
     qn.rc_pr = __frcp_rn(qn.pr);
     qn.rc_opb = __frcp_rn(P.one_plus_bias);
     qn.slow = !(qn.pr > 1e-18f && qn.pr < 1e18f);
+    VG_TR(1);
 
     // ---- phase 2: quantise; per-slice counts and occupied rows / columns; counting sort by slice ----
     uint2 *tmp = reinterpret_cast<uint2 *>(sm.B);      // unsorted (x | y << 8 | slice << 16 | rank << 19, value)
@@ -1135,6 +1162,7 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
         }
     }
     __syncthreads();
+    VG_TR(2);
     if (tid < 2 * D) {
         const int d = tid >> 1;
         const bool rows = (tid & 1) == 0;
@@ -1157,7 +1185,30 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
         for (int d = 0; d < tid - 32; ++d) acc += sm.cnt[d];
         sm.base[tid - 32] = acc;
     }
+    {
+        // counting sort: every thread forms the slice offsets itself (eight 16-bit prefixes in two
+        // registers), so the sorted cache is complete at the same barrier as the ranges
+        unsigned long long plo = 0ull, phi = 0ull;
+        unsigned acc = 0u;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            if (d < 4) plo |= (unsigned long long)acc << (16 * d);
+            else phi |= (unsigned long long)acc << (16 * (d - 4));
+            acc += (unsigned)sm.cnt[d];
+        }
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            const int i = tid + k * NTF;
+            if (i < n) {
+                const uint2 e = tmp[i];
+                const unsigned zi = (e.x >> 16) & 7u;
+                const unsigned base = (unsigned)(((zi & 4u) ? phi : plo) >> (16 * (zi & 3u))) & 0xffffu;
+                sm.cache[base + (e.x >> 19)] = make_uint2(e.x & 0xffffu, e.y);
+            }
+        }
+    }
     __syncthreads();
+    VG_TR(3);
     const int ulo = sm.ulo, uhi = sm.uhi, vlo = sm.vlo, vhi = sm.vhi;   // image cells any slice writes
     const int nr = uhi - ulo + 1;
     const int us_lo = vlo >> 2, ns = (vhi >> 2) - us_lo + 1;
@@ -1165,27 +1216,15 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
     if (nr > F_MAXR || ns > F_MAXS || npair > KQ * NTF) { hand_over(); return; }    // block-uniform
     if (P.status && v == 0 && tid == 0) P.status[c] = VG_OK;
     const ProjTables *__restrict__ tab = P.tab;
-    if (tid < S) {
-        const int y0 = sm.i0[tid];
-        const int y1 = y0 + (y0 < Q - 1 ? 1 : 0);
-        if (!(y1 < ulo || y0 > uhi)) { atomicMin(&sm.oy_lo, tid); atomicMax(&sm.oy_hi, tid); }
-    } else if (tid < S + NG) {
-        const int g = tid - S;
-        const int xa = sm.i0[8 * g];
-        int xb = sm.i0[8 * g + 7];
-        xb += xb < Q - 1 ? 1 : 0;
-        if (!(xb < vlo || xa > vhi)) { atomicMin(&sm.g_lo, g); atomicMax(&sm.g_hi, g); }
-    }
-#pragma unroll
-    for (int k = 0; k < KP; ++k) {
-        const int i = tid + k * NTF;
-        if (i < n) {
-            const uint2 e = tmp[i];
-            sm.cache[sm.base[(e.x >> 16) & 7u] + (int)(e.x >> 19)] = make_uint2(e.x & 0xffffu, e.y);
-        }
-    }
-    __syncthreads();
-    const int oy_lo = sm.oy_lo, oy_hi = sm.oy_hi, g_lo = sm.g_lo, g_hi = sm.g_hi;
+    // Output rows / 8-pixel column groups with a source pixel inside the touched region, in closed form:
+    // the first source row of output row oy is i0[oy] = floor(oy (Q-1) / (S-1)) (projection_init checks
+    // the table against this), the second one i0 + 1, so
+    //   row oy is active     <=>  ulo - 1 <= i0[oy] <= uhi
+    //   group g is active    <=>  i0[8 g + 7] >= vlo - 1  and  i0[8 g] <= vhi
+    // and i0[o] >= t  <=>  o >= ceil(t (S-1) / (Q-1)).
+    auto first_with = [](int t) { return t <= 0 ? 0 : (t * (S - 1) + (Q - 2)) / (Q - 1); };
+    const int oy_lo = first_with(ulo - 1), oy_hi = min(first_with(uhi + 1) - 1, S - 1);
+    const int g_lo = first_with(vlo - 1) >> 3, g_hi = min(min(first_with(vhi + 1) - 1, S - 1) >> 3, NG - 1);
     // buffer coordinates: grid row y -> y + orow, grid column x -> x + ocol (float index inside a row)
     const int orow = 1 - ulo, ocol = 4 * (2 - us_lo);
 
@@ -1202,9 +1241,11 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
             const int gg = 2 * (warp + j * NWF) + half;
             colact[j] = gg >= g_lo && gg <= g_hi;
         }
+        const bool splat = P.bg_splat != 0u;       // R = 112: the background is one value, nothing to load
         if (tile) {
             const uint4 *__restrict__ src = tab->bg_tile + tid;
             uint4 *dst = reinterpret_cast<uint4 *>(tile) + tid;
+            const uint4 bgv = make_uint4(P.bg_splat, P.bg_splat, P.bg_splat, P.bg_splat);
 #pragma unroll 7
             for (int py = 0; py < 14; ++py) {
                 const int oy = 16 * py + ky;
@@ -1212,7 +1253,7 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
 #pragma unroll
                 for (int j = 0; j < NPX; ++j)
                     if (warp + j * NWF < 14 && !(rowact && colact[j]))
-                        dst[py * 448 + j * NTF] = __ldg(src + py * 448 + j * NTF);
+                        dst[py * 448 + j * NTF] = splat ? bgv : __ldg(src + py * 448 + j * NTF);
             }
         }
         if (u8) {
@@ -1223,12 +1264,15 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
                 for (int j = 0; j < NPX; ++j) {
                     const int gg = 2 * (warp + j * NWF) + half;
                     if (warp + j * NWF < 14 && !(rowact && colact[j]))
-                        *reinterpret_cast<uint2 *>(u8 + oy * S + 8 * gg) = __ldg(&tab->bg_u8[(oy * S + 8 * gg) >> 3]);
+                        *reinterpret_cast<uint2 *>(u8 + oy * S + 8 * gg) =
+                            splat ? make_uint2(P.bg_u8_splat, P.bg_u8_splat)
+                                  : __ldg(&tab->bg_u8[(oy * S + 8 * gg) >> 3]);
                 }
             }
         }
     }
 
+    VG_TR(4);
     // ---- phase 3: per occupied slice: stamp the 5x5 footprints, 3x3 Gaussian, depth max ------------
     // item k of a thread: rows (2 yp, 2 yp + 1) of the union x strip su; img0 / img1 = their running maxima
     float4 img0[KQ], img1[KQ];
@@ -1246,6 +1290,8 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
         img1[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const float (&w)[9] = P.gauss;
+    VG_TR(5);
+    VG_TR_ON(long long tr_clear = 0; long long tr_stamp = 0; long long tr_gauss = 0; long long tr_t = 0;)
     unsigned occ = 0u;         // occupied depth slices
 #pragma unroll
     for (int d = 0; d < D; ++d) occ |= sm.cnt[d] > 0 ? 1u << d : 0u;
@@ -1256,9 +1302,11 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
         if (!first) __syncthreads();       // every Gaussian read of the previous slice is done
         first = false;
         const int ylo = sm.ylo[d], yhi = sm.yhi[d], xlo = sm.xlo[d], xhi = sm.xhi[d];
+        VG_TR_ON(if (P.trace) tr_t = clock64();)
         if (lane < F_PITCH)
             for (int r = warp; r < nr + 3; r += NWF) sm.B[r * F_PITCH + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
+        VG_TR_ON(if (P.trace) { const long long t = clock64(); tr_clear += t - tr_t; tr_t = t; })
         {
             // one item = one row of one point's 5x5 footprint (see project_image); all values are
             // positive floats: integer order == float order
@@ -1289,6 +1337,7 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
             }
         }
         __syncthreads();
+        VG_TR_ON(if (P.trace) { const long long t = clock64(); tr_stamp += t - tr_t; tr_t = t; })
         {
             // smoothed rows of this slice: [gy0, gy1]; a pair takes part when one of its rows is inside
             const int gy0 = max(ylo - 4, 0), gy1 = min(yhi + 2, Q - 1);
@@ -1322,7 +1371,12 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
                 }
             }
         }
+        VG_TR_ON(if (P.trace) tr_gauss += clock64() - tr_t;)
     }
+    VG_TR(6);
+    VG_TR_ON(if (P.trace && tid == 0 && b < kTraceImages) {
+        P.trace[b * 12 + 9] = tr_clear; P.trace[b * 12 + 10] = tr_stamp; P.trace[b * 12 + 11] = tr_gauss;
+    })
 
     // ---- phase 4: img / max(img), 1 - x; the normalised image goes back into B, margins = 1.0 ------
     {
@@ -1374,6 +1428,7 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
             }
         }
         __syncthreads();
+        VG_TR(7);
         if (P.dbg_dens) {
             float *dd = P.dbg_dens + (size_t)b * Q * Q;
             const float *Bf = reinterpret_cast<const float *>(sm.B);
@@ -1409,21 +1464,26 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
         while (oy > oy_lo && (int)sm.i0[oy - 1] >= ys) --oy;
         while ((int)sm.i0[oy] < ys) ++oy;                                // i0 reaches yb >= ys at oy_hi
         oy = max(oy, oy_lo);
-        const float *Bf = reinterpret_cast<const float *>(sm.B) + orow * PW + ocol;
-        int xo[8];
+        // shared-window byte address of B[row 0][x0 of output column 8 g + j]: a source row is one add away
+        const unsigned b0 = (unsigned)__cvta_generic_to_shared(sm.B) + 4u * (unsigned)(orow * PW + ocol);
+        unsigned xa[8];
         float lw0[8], lw1[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            xo[j] = sm.i0[8 * g + j];
+            xa[j] = b0 + 4u * sm.i0[8 * g + j];
             const float2 t = sm.lw[8 * g + j];
             lw0[j] = t.x; lw1[j] = t.y;
         }
         float ha[8], hb[8];
         auto hrow = [&](int y, float (&h)[8]) {
-            const float *row = Bf + y * PW;
+            const unsigned ro = (unsigned)(y * (4 * PW));
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                h[j] = __fmaf_rn(row[xo[j]], lw0[j], __fmul_rn(row[xo[j] + 1], lw1[j]));
+            for (int j = 0; j < 8; ++j) {
+                float v0, v1;
+                asm volatile("ld.shared.f32 %0, [%2];\n\tld.shared.f32 %1, [%2 + 4];"
+                             : "=f"(v0), "=f"(v1) : "r"(xa[j] + ro));
+                h[j] = __fmaf_rn(v0, lw0[j], __fmul_rn(v1, lw1[j]));
+            }
         };
         const f32x2 k255 = pack2(255.0f, 255.0f), kmagic = pack2(8388608.0f, 8388608.0f);
         op_t *tdst = tile ? tile + (g >> 1) * 256 + (g & 1) * 8 : nullptr;
@@ -1474,6 +1534,7 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
                 ++oy;
             }
         }
+        VG_TR(8);
     }
 }
 
@@ -1494,6 +1555,31 @@ int launch_fast_t(VgHandle *h, const ProjParams &P, long long blocks, cudaStream
     if (rc) return rc;
     projection_fast_kernel<NTF, MINB><<<(unsigned)blocks, NTF, sizeof(FastSmem), st>>>(P);
     return VG_OK;
+}
+
+// VG_PROJ_TRACE=1: mean cycles thread 0 of a CTA spends in each phase of the fast kernel (debug aid)
+void print_trace(VgHandle *h, int images, cudaStream_t st)
+{
+    cudaStreamSynchronize(st);
+    std::vector<long long> t((size_t)images * 12);
+    cudaMemcpy(t.data(), h->proj_trace, t.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    const char *names[8] = {"phase 1 (rotate, min/max)", "quantise + atomics", "ranges, sort", "background",
+                            "item setup", "slices", "normalise, write back", "emit (thread 0)"};
+    double sum[8] = {0}, sl[3] = {0}, total = 0;
+    int cnt = 0;
+    for (int i = 0; i < images; ++i) {
+        const long long *r = &t[(size_t)i * 12];
+        if (r[0] == 0 || r[8] <= r[0]) continue;       // handed over / degenerate / idle thread 0
+        for (int k = 0; k < 8; ++k) sum[k] += (double)(r[k + 1] - r[k]);
+        for (int k = 0; k < 3; ++k) sl[k] += (double)r[9 + k];
+        total += (double)(r[8] - r[0]);
+        ++cnt;
+    }
+    if (!cnt) return;
+    fprintf(stderr, "projection_fast_kernel trace: %d images, mean %.0f cycles per CTA\n", cnt, total / cnt);
+    for (int k = 0; k < 8; ++k) fprintf(stderr, "  %-28s %8.0f  %5.1f %%\n", names[k], sum[k] / cnt, 100 * sum[k] / total);
+    fprintf(stderr, "  slices: clear %.0f, stamp %.0f, gauss %.0f\n", sl[0] / cnt, sl[1] / cnt, sl[2] / cnt);
+    cudaMemset(h->proj_trace, 0, t.size() * sizeof(long long));
 }
 
 constexpr long long kDeferCap = 1ll << 20;     // images per fast launch (capacity of the hand-over list)
@@ -1520,6 +1606,28 @@ int projection_init(VgHandle *h)
     VG_CUDA_CHECK(h, cudaMemset(h->proj_spill_flags, 0, slots * sizeof(int)));
     if (R == 224)    // running depth-max image of the one CTA resident on each SM (~29 MB)
         VG_CUDA_CHECK(h, cudaMalloc(&h->proj_img_scratch, (size_t)nsmid * Q * R * sizeof(float)));
+    // the fast kernel writes the background as a constant when the whole tile is one value (R = 112:
+    // 255 everywhere), and derives the active output rows / columns from i0[o] = floor(o (Q-1) / (S-1))
+    {
+        std::vector<ProjTables> host(1);
+        VG_CUDA_CHECK(h, cudaMemcpy(host.data(), t, sizeof(ProjTables), cudaMemcpyDeviceToHost));
+        const uint16_t *bt = reinterpret_cast<const uint16_t *>(host[0].bg_tile);
+        const uint8_t *bu = reinterpret_cast<const uint8_t *>(host[0].bg_u8);
+        bool uniform = true;
+        for (int i = 1; i < VG_TILE_ELEMS && uniform; ++i) uniform = bt[i] == bt[0];
+        for (int i = 1; i < S * S && uniform; ++i) uniform = bu[i] == bu[0];
+        h->proj_bg_splat = uniform && bt[0] != 0 ? ((uint32_t)bt[0] << 16) | bt[0] : 0u;
+        h->proj_bg_u8_splat = 0x01010101u * bu[0];
+        h->proj_table_exact = true;
+        for (int o = 0; o < S; ++o)
+            if (host[0].i0[o] != (o * (Q - 1)) / (S - 1)) h->proj_table_exact = false;
+    }
+#ifdef VG_PROJ_TRACE
+    if (getenv("VG_PROJ_TRACE")) {
+        VG_CUDA_CHECK(h, cudaMalloc(&h->proj_trace, (size_t)kTraceImages * 12 * sizeof(long long)));
+        VG_CUDA_CHECK(h, cudaMemset(h->proj_trace, 0, (size_t)kTraceImages * 12 * sizeof(long long)));
+    }
+#endif
     // hand-over list of the fast kernel (count + image indices, 4 MB)
     VG_CUDA_CHECK(h, cudaMalloc(&h->proj_defer, (size_t)(kDeferCap + 1) * sizeof(int32_t)));
     // The fast kernel's shared-memory layout covers touched regions of F_MAXR rows x F_MAXS strips.
@@ -1532,7 +1640,7 @@ int projection_init(VgHandle *h)
         const int hi = (int)std::min((double)(R - 2), std::ceil((1.0 + rho) * 0.5 * R + 1e-3));
         const int rows = std::min(hi + 2, Q - 1) - std::max(lo - 4, 0) + 1;
         const int strips = (std::min(hi + 2, Q - 1) >> 2) - (std::max(lo - 4, 0) >> 2) + 1;
-        h->proj_fast = R == 112 && rows <= F_MAXR && strips <= F_MAXS;
+        h->proj_fast = R == 112 && rows <= F_MAXR && strips <= F_MAXS && h->proj_table_exact;
     }
     VG_CUDA_CHECK(h, cudaDeviceSynchronize());
     return VG_OK;
@@ -1574,6 +1682,9 @@ int launch_projection(VgHandle *h, const float *d_points, const int32_t *d_offse
     P.dbg_dens = dbg ? dbg->d_densified : nullptr;
     P.defer = static_cast<int32_t *>(h->proj_defer);
     P.block0 = 0;
+    P.trace = h->proj_trace;
+    P.bg_splat = h->proj_bg_splat;
+    P.bg_u8_splat = h->proj_bg_u8_splat;
     const long long blocks = (long long)C * cfg.num_views;
     // algorithmic bytes recorded here: the emitted tiles; the caller adds 12 * sum(N) for the points
     VgProfScope prof(h, VG_K_PROJECTION, (double)blocks * VG_TILE_ELEMS * 2.0, st);
@@ -1595,6 +1706,7 @@ int launch_projection(VgHandle *h, const float *d_points, const int32_t *d_offse
             if ((rc = launch_projection_t<112, true>(h, P, std::min<long long>(nb, 2ll * h->num_sms), st))) return rc;
             VG_LAUNCH_CHECK(h);
         }
+        if (P.trace) print_trace(h, (int)std::min<long long>(blocks, kTraceImages), st);
         return VG_OK;
     }
     rc = cfg.resolution == 112 ? launch_projection_t<112, false>(h, P, blocks, st)
