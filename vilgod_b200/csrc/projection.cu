@@ -1019,9 +1019,21 @@ struct FastSmem {
     int ulo, uhi, vlo, vhi;
     float red[32];
     int degenerate;
+    uint4 bgsrc[448];      // one patch row (14 patches x 512 B) of background pixels: source of the bulk stores
     float2 lw[S];          // bilinear weights (l0, l1) of output row / column i ...
     unsigned char i0[S];   // ... and its first source row / column (copy of ProjTables, filled per CTA)
 };
+
+// shared -> global bulk copy (TMA, no tensor map): the copy engine reads shared memory and writes L2
+// without passing through the load/store unit
+__device__ __forceinline__ void bulk_store(void *gdst, unsigned ssrc, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // phase timeline of the fast kernel: compiled in only with -DVG_PROJ_TRACE (python -m vilgod_b200.build
 // --trace -> libvilgod_b200_trace.so); the counters would otherwise cost registers in the slice loop
@@ -1041,7 +1053,6 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
 {
     constexpr int R = 112, Q = R - 2, NS = R / 4, MW = 4;
     constexpr int NWF = NTF / 32;
-    constexpr int KP = (FAST_N + NTF - 1) / NTF;                        // points per thread
     constexpr int KQ = ((F_MAXR / 2) * F_MAXS + NTF - 1) / NTF;         // (row pair, strip) items per thread
     constexpr int PW = 4 * F_PITCH;                                     // buffer pitch in floats
     static_assert(NTF >= S && NTF >= 64, "setup roles are mapped to thread ids");
@@ -1066,34 +1077,39 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
         sm.degenerate = 0;
         sm.ulo = Q; sm.uhi = -1; sm.vlo = Q; sm.vhi = -1;
     }
+    if (P.bg_splat != 0u && P.tiles)
+        for (int i = tid; i < 448; i += NTF) sm.bgsrc[i] = make_uint4(P.bg_splat, P.bg_splat, P.bg_splat, P.bg_splat);
     const int beg = P.offsets[c];
     const int n = P.offsets[c + 1] - beg;
+    __syncthreads();
     auto hand_over = [&]() {
         if (tid == 0) P.defer[1 + atomicAdd(P.defer, 1)] = b;
     };
     if (n > FAST_N) { hand_over(); return; }
     VG_TR(0);
-    __syncthreads();
     const float *__restrict__ pts = P.points + 3 * (size_t)beg;
     const float *rm = P.rot + 9 * v;
     const bool fused = P.rotate_mode == VG_ROTATE_FUSED ||
                        (P.rotate_mode == VG_ROTATE_TORCH_CPU && 9 * (long long)n >= 400);
 
-    // ---- phase 1: rotate (kept in registers), per-axis min / max ---------------------------------
-    float qx[KP], qy[KP], qz[KP];
+    // ---- phase 1: rotate, per-axis min / max.  The rotated points wait in shared memory (the buffer B
+    // is free until the first slice) so that this loop and the next one stay rolled: small code, no
+    // register arrays ---------------------------------------------------------------------------------
+    float *qxs = reinterpret_cast<float *>(sm.B), *qys = qxs + FAST_N, *qzs = qys + FAST_N;
+    uint2 *tmp = reinterpret_cast<uint2 *>(qzs + FAST_N);   // unsorted (x | y << 8 | slice << 16 | rank << 19, value)
+    static_assert(FAST_N * 20 <= sizeof(sm.B), "staging of the points must fit the slice buffer");
     {
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY;
         float mn0 = INFINITY, mn1 = INFINITY, mn2 = INFINITY;
         bool finite = true;
-#pragma unroll
-        for (int k = 0; k < KP; ++k) {
-            const int i = tid + k * NTF;
-            if (i < n) {
-                rotate_point(pts + 3 * i, rm, fused, qx[k], qy[k], qz[k]);
-                finite = finite && isfinite(qx[k]) && isfinite(qy[k]) && isfinite(qz[k]);
-                mx0 = fmaxf(mx0, qx[k]); mx1 = fmaxf(mx1, qy[k]); mx2 = fmaxf(mx2, qz[k]);
-                mn0 = fminf(mn0, qx[k]); mn1 = fminf(mn1, qy[k]); mn2 = fminf(mn2, qz[k]);
-            }
+#pragma unroll 1
+        for (int i = tid; i < n; i += NTF) {
+            float qx, qy, qz;
+            rotate_point(pts + 3 * i, rm, fused, qx, qy, qz);
+            qxs[i] = qx; qys[i] = qy; qzs[i] = qz;
+            finite = finite && isfinite(qx) && isfinite(qy) && isfinite(qz);
+            mx0 = fmaxf(mx0, qx); mx1 = fmaxf(mx1, qy); mx2 = fmaxf(mx2, qz);
+            mn0 = fminf(mn0, qx); mn1 = fminf(mn1, qy); mn2 = fminf(mn2, qz);
         }
         const unsigned k0 = __reduce_max_sync(0xffffffffu, f2key(mx0));
         const unsigned k1 = __reduce_max_sync(0xffffffffu, f2key(mx1));
@@ -1147,19 +1163,15 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
     VG_TR(1);
 
     // ---- phase 2: quantise; per-slice counts and occupied rows / columns; counting sort by slice ----
-    uint2 *tmp = reinterpret_cast<uint2 *>(sm.B);      // unsorted (x | y << 8 | slice << 16 | rank << 19, value)
-#pragma unroll
-    for (int k = 0; k < KP; ++k) {
-        const int i = tid + k * NTF;
-        if (i < n) {
-            float val; int X, Y, zi;
-            quantise<R>(qx[k], qy[k], qz[k], qn, P, X, Y, zi, val);
-            atomicOr(&sm.rowmask[zi][Y >> 5], 1u << (Y & 31));
-            atomicOr(&sm.colmask[zi][X >> 5], 1u << (X & 31));
-            const unsigned rank = (unsigned)atomicAdd(&sm.cnt[zi], 1);
-            tmp[i] = make_uint2((unsigned)X | ((unsigned)Y << 8) | ((unsigned)zi << 16) | (rank << 19),
-                                __float_as_uint(val));
-        }
+#pragma unroll 1
+    for (int i = tid; i < n; i += NTF) {
+        float val; int X, Y, zi;
+        quantise<R>(qxs[i], qys[i], qzs[i], qn, P, X, Y, zi, val);
+        atomicOr(&sm.rowmask[zi][Y >> 5], 1u << (Y & 31));
+        atomicOr(&sm.colmask[zi][X >> 5], 1u << (X & 31));
+        const unsigned rank = (unsigned)atomicAdd(&sm.cnt[zi], 1);
+        tmp[i] = make_uint2((unsigned)X | ((unsigned)Y << 8) | ((unsigned)zi << 16) | (rank << 19),
+                            __float_as_uint(val));
     }
     __syncthreads();
     VG_TR(2);
@@ -1196,15 +1208,12 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
             else phi |= (unsigned long long)acc << (16 * (d - 4));
             acc += (unsigned)sm.cnt[d];
         }
-#pragma unroll
-        for (int k = 0; k < KP; ++k) {
-            const int i = tid + k * NTF;
-            if (i < n) {
-                const uint2 e = tmp[i];
-                const unsigned zi = (e.x >> 16) & 7u;
-                const unsigned base = (unsigned)(((zi & 4u) ? phi : plo) >> (16 * (zi & 3u))) & 0xffffu;
-                sm.cache[base + (e.x >> 19)] = make_uint2(e.x & 0xffffu, e.y);
-            }
+#pragma unroll 1
+        for (int i = tid; i < n; i += NTF) {
+            const uint2 e = tmp[i];
+            const unsigned zi = (e.x >> 16) & 7u;
+            const unsigned base = (unsigned)(((zi & 4u) ? phi : plo) >> (16 * (zi & 3u))) & 0xffffu;
+            sm.cache[base + (e.x >> 19)] = make_uint2(e.x & 0xffffu, e.y);
         }
     }
     __syncthreads();
@@ -1228,24 +1237,56 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
     // buffer coordinates: grid row y -> y + orow, grid column x -> x + ocol (float index inside a row)
     const int orow = 1 - ulo, ocol = 4 * (2 - us_lo);
 
-    // ---- background: every 16-byte piece of the tile outside the active rows x column groups is a copy
-    // of the precomputed background tile.  A warp owns the patch columns px = warp, warp + NWF, a lane the
-    // piece (row ky, half) of a patch, so the column test is loop invariant and a patch row costs one
-    // row test plus a load / store per owned patch ------------------------------------------------------
+    // ---- background: every 16-byte piece of the tile outside the active rows x column groups holds the
+    // background value.  R = 112 (one value everywhere): whole patch rows above / below the active patches
+    // and the runs of patches left / right of them go out as bulk stores from a constant patch row in
+    // shared memory (at most two per patch row, issued by one lane per warp: ~80 KB per image that never touch the
+    // load/store unit); only the pieces of the border patches are written by the lanes.  Otherwise
+    // (background tile with a pattern): a warp owns the patch columns px = warp, warp + NWF, a lane the
+    // piece (row ky, half) of a patch, and copies from the precomputed tile --------------------------------
     {
         const int ky = lane >> 1, half = lane & 1;
+        const bool splat = P.bg_splat != 0u;
         constexpr int NPX = (14 + NWF - 1) / NWF;
-        bool colact[NPX];
+        if (tile && splat) {
+            const int py_a = oy_lo >> 4, py_b = oy_hi >> 4, px_a = g_lo >> 1, px_b = g_hi >> 1;
+            if (lane == 0) {                // one issuing thread per warp, patch rows py = warp, warp + NWF
+                fence_async_smem();         // the constant row was written through the generic proxy
+                const unsigned src = (unsigned)__cvta_generic_to_shared(sm.bgsrc);
+                for (int py = warp; py < 14; py += NWF) {
+                    char *rowp = reinterpret_cast<char *>(tile) + py * 7168;
+                    if (py < py_a || py > py_b) {
+                        bulk_store(rowp, src, 7168u);
+                    } else {
+                        if (px_a > 0) bulk_store(rowp, src, (unsigned)px_a * 512u);
+                        if (px_b < 13) bulk_store(rowp + (px_b + 1) * 512, src, (unsigned)(13 - px_b) * 512u);
+                    }
+                }
+                bulk_commit();
+            }
+            uint4 *dst = reinterpret_cast<uint4 *>(tile) + lane;
+            const uint4 bgv = make_uint4(P.bg_splat, P.bg_splat, P.bg_splat, P.bg_splat);
+            auto piece = [&](int py, int px) {
+                const int oy = 16 * py + ky, gg = 2 * px + half;
+                if (!(oy >= oy_lo && oy <= oy_hi && gg >= g_lo && gg <= g_hi)) dst[(py * 14 + px) * 32] = bgv;
+            };
+            for (int px = px_a + warp; px <= px_b; px += NWF) {          // top / bottom border patches
+                piece(py_a, px);
+                if (py_b != py_a) piece(py_b, px);
+            }
+            for (int py = py_a + 1 + warp; py < py_b; py += NWF) {       // left / right border patches
+                piece(py, px_a);
+                if (px_b != px_a) piece(py, px_b);
+            }
+        } else if (tile) {
+            bool colact[NPX];
 #pragma unroll
-        for (int j = 0; j < NPX; ++j) {
-            const int gg = 2 * (warp + j * NWF) + half;
-            colact[j] = gg >= g_lo && gg <= g_hi;
-        }
-        const bool splat = P.bg_splat != 0u;       // R = 112: the background is one value, nothing to load
-        if (tile) {
+            for (int j = 0; j < NPX; ++j) {
+                const int gg = 2 * (warp + j * NWF) + half;
+                colact[j] = gg >= g_lo && gg <= g_hi;
+            }
             const uint4 *__restrict__ src = tab->bg_tile + tid;
             uint4 *dst = reinterpret_cast<uint4 *>(tile) + tid;
-            const uint4 bgv = make_uint4(P.bg_splat, P.bg_splat, P.bg_splat, P.bg_splat);
 #pragma unroll 7
             for (int py = 0; py < 14; ++py) {
                 const int oy = 16 * py + ky;
@@ -1253,7 +1294,7 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
 #pragma unroll
                 for (int j = 0; j < NPX; ++j)
                     if (warp + j * NWF < 14 && !(rowact && colact[j]))
-                        dst[py * 448 + j * NTF] = splat ? bgv : __ldg(src + py * 448 + j * NTF);
+                        dst[py * 448 + j * NTF] = __ldg(src + py * 448 + j * NTF);
             }
         }
         if (u8) {
@@ -1263,7 +1304,7 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
 #pragma unroll
                 for (int j = 0; j < NPX; ++j) {
                     const int gg = 2 * (warp + j * NWF) + half;
-                    if (warp + j * NWF < 14 && !(rowact && colact[j]))
+                    if (warp + j * NWF < 14 && !(rowact && gg >= g_lo && gg <= g_hi))
                         *reinterpret_cast<uint2 *>(u8 + oy * S + 8 * gg) =
                             splat ? make_uint2(P.bg_u8_splat, P.bg_u8_splat)
                                   : __ldg(&tab->bg_u8[(oy * S + 8 * gg) >> 3]);
@@ -1427,6 +1468,8 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
                 if (o / F_PITCH + 1 <= nr) sm.B[o + F_PITCH] = norm4(img1[k]);
             }
         }
+        if (lane == 0) bulk_wait_read();   // the bulk stores have read their source long ago; no thread may
+                                           // exit before that is certain
         __syncthreads();
         VG_TR(7);
         if (P.dbg_dens) {
