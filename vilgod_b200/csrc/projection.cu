@@ -1048,7 +1048,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 #define VG_TR_ON(x)
 #endif
 
-template <int NTF, int MINB>
+template <int NTF, int MINB, int CW>
 __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjParams P)
 {
     constexpr int R = 112, Q = R - 2, NS = R / 4, MW = 4;
@@ -1344,8 +1344,15 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
         first = false;
         const int ylo = sm.ylo[d], yhi = sm.yhi[d], xlo = sm.xlo[d], xhi = sm.xhi[d];
         VG_TR_ON(if (P.trace) tr_t = clock64();)
-        if (lane < F_PITCH)
-            for (int r = warp; r < nr + 3; r += NWF) sm.B[r * F_PITCH + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // clear what this slice's Gaussian can read: the pairs overlapping the smoothed rows [gy0, gy1]
+        // read buffer rows gy0 - 2 .. gy1 + 2, strips 1 .. ns + 2 (everything else is not looked at before
+        // the normalised image overwrites it)
+        {
+            const int r_lo = max(max(ylo - 4, 0) + orow - 2, 0), r_hi = min(min(yhi + 2, Q - 1) + orow + 2, nr + 2);
+            if (lane < ns + 3)
+                for (int r = r_lo + warp; r <= r_hi; r += NWF)
+                    sm.B[r * F_PITCH + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         __syncthreads();
         VG_TR_ON(if (P.trace) { const long long t = clock64(); tr_clear += t - tr_t; tr_t = t; })
         {
@@ -1353,13 +1360,14 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
             // positive floats: integer order == float order
             int *Bi = reinterpret_cast<int *>(sm.B) + orow * PW + ocol - 3 * PW - 3;
             const uint2 *cache = sm.cache + sm.base[d];
-            if (xlo >= 3 && xhi <= Q - 2 && ylo >= 3 && yhi <= Q - 2) {      // no footprint leaves the image
-                for (int item = tid; item < 5 * cnt; item += NTF) {
-                    const int p = (item * 13108) >> 16, dy = item - 5 * p;     // item / 5 for item < 10,240
+            if (xlo >= 3 && xhi <= Q - 2 && ylo >= 3 && yhi <= Q - 2) {      // no footprint leaves the image:
+                for (int p = tid; p < cnt; p += NTF) {                       // a thread stamps a whole footprint
                     const uint2 e = cache[p];
-                    int *row = Bi + ((int)(e.x >> 8) + dy) * PW + (int)(e.x & 255u);
+                    int *row = Bi + (int)(e.x >> 8) * PW + (int)(e.x & 255u);
 #pragma unroll
-                    for (int dx = 0; dx < 5; ++dx) atomicMax(row + dx, (int)e.y);
+                    for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+                        for (int dx = 0; dx < 5; ++dx) atomicMax(row + dy * PW + dx, (int)e.y);
                 }
             } else {
                 for (int item = tid; item < 5 * cnt; item += NTF) {
@@ -1491,14 +1499,17 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
     // step further, so the unclamped read gives the same +0 product.)
     if (oy_hi < oy_lo || g_hi < g_lo) return;
     {
-        const int ng = g_hi - g_lo + 1;
-        const int nseg = small_div(NTF, ng);
-        const int seg = small_div(tid, ng);
+        // a thread owns CW adjacent output columns and a run of SOURCE rows [ys, ye]: per source row one
+        // horizontal interpolation (the row below is carried over in registers) and the two or three output
+        // rows whose upper source row it is.  CW = 4: consecutive lanes read consecutive source pixels
+        // (few bank conflicts: the shared-memory pipe is this kernel's busiest unit) and a row costs one
+        // 8-byte store
+        constexpr int CP = CW / 2;                                       // packed column pairs
+        const int ncg = (g_hi - g_lo + 1) * (8 / CW);                    // column sets of the active groups
+        const int nseg = small_div(NTF, ncg);
+        const int seg = small_div(tid, ncg);
         if (seg >= nseg) return;
-        const int g = g_lo + (tid - seg * ng);
-        // a thread owns column group g and a run of SOURCE rows [ys, ye]: per source row one horizontal
-        // interpolation (the row below is carried over) and the two or three output rows whose upper
-        // source row it is
+        const int ox0 = 8 * g_lo + CW * (tid - seg * ncg);
         const int ya = sm.i0[oy_lo], yb = sm.i0[oy_hi];
         const int len = small_div(yb - ya + nseg, nseg);
         const int ys = ya + seg * len, ye = min(ys + len - 1, yb);
@@ -1507,43 +1518,44 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
         while (oy > oy_lo && (int)sm.i0[oy - 1] >= ys) --oy;
         while ((int)sm.i0[oy] < ys) ++oy;                                // i0 reaches yb >= ys at oy_hi
         oy = max(oy, oy_lo);
-        // shared-window byte address of B[row 0][x0 of output column 8 g + j]: a source row is one add away
+        // shared-window byte address of B[row 0][x0 of output column ox0 + j]: a source row is one add away
         const unsigned b0 = (unsigned)__cvta_generic_to_shared(sm.B) + 4u * (unsigned)(orow * PW + ocol);
-        unsigned xa[8];
-        float lw0[8], lw1[8];
+        unsigned xa[CW];
+        f32x2 lw0[CP], lw1[CP];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            xa[j] = b0 + 4u * sm.i0[8 * g + j];
-            const float2 t = sm.lw[8 * g + j];
-            lw0[j] = t.x; lw1[j] = t.y;
+        for (int j = 0; j < CP; ++j) {
+            xa[2 * j] = b0 + 4u * sm.i0[ox0 + 2 * j];
+            xa[2 * j + 1] = b0 + 4u * sm.i0[ox0 + 2 * j + 1];
+            const float2 ta = sm.lw[ox0 + 2 * j], tb = sm.lw[ox0 + 2 * j + 1];
+            lw0[j] = pack2(ta.x, tb.x);
+            lw1[j] = pack2(ta.y, tb.y);
         }
-        float ha[8], hb[8];
-        auto hrow = [&](int y, float (&h)[8]) {
+        f32x2 ha[CP], hb[CP];
+        auto hrow = [&](int y, f32x2 (&h)[CP]) {
             const unsigned ro = (unsigned)(y * (4 * PW));
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float v0, v1;
+            for (int j = 0; j < CP; ++j) {
+                float a0, a1, c0, c1;
                 asm volatile("ld.shared.f32 %0, [%2];\n\tld.shared.f32 %1, [%2 + 4];"
-                             : "=f"(v0), "=f"(v1) : "r"(xa[j] + ro));
-                h[j] = __fmaf_rn(v0, lw0[j], __fmul_rn(v1, lw1[j]));
+                             : "=f"(a0), "=f"(a1) : "r"(xa[2 * j] + ro));
+                asm volatile("ld.shared.f32 %0, [%2];\n\tld.shared.f32 %1, [%2 + 4];"
+                             : "=f"(c0), "=f"(c1) : "r"(xa[2 * j + 1] + ro));
+                h[j] = fma2(pack2(a0, c0), lw0[j], mul2(pack2(a1, c1), lw1[j]));
             }
         };
         const f32x2 k255 = pack2(255.0f, 255.0f), kmagic = pack2(8388608.0f, 8388608.0f);
-        op_t *tdst = tile ? tile + (g >> 1) * 256 + (g & 1) * 8 : nullptr;
-        hrow(ys, hb);
+        op_t *tdst = tile ? tile + (ox0 >> 4) * 256 + (ox0 & 15) : nullptr;
         int ynext = sm.i0[oy];             // upper source row of output row oy, loaded one row ahead
-        for (int y = ys; y <= ye; ++y) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) ha[j] = hb[j];
-            hrow(y + 1, hb);
+        // the output rows whose upper source row is y, from top = HI[y] and bot = HI[y + 1]
+        auto emit_rows = [&](int y, const f32x2 (&top)[CP], const f32x2 (&bot)[CP]) {
             while (oy <= oy_hi && ynext == y) {
                 const float2 lh = sm.lw[oy];
                 ynext = sm.i0[min(oy + 1, S - 1)];
                 const f32x2 h0 = pack2(lh.x, lh.x), h1 = pack2(lh.y, lh.y);
-                unsigned fb[8];
+                unsigned fb[CW];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const f32x2 o = fma2(pack2(ha[2 * j], ha[2 * j + 1]), h0, mul2(pack2(hb[2 * j], hb[2 * j + 1]), h1));
+                for (int j = 0; j < CP; ++j) {
+                    const f32x2 o = fma2(top[j], h0, mul2(bot[j], h1));
                     const f32x2 q = sub2(add2_rz(mul2(o, k255), kmagic), kmagic);
                     float q0, q1;
                     unpack2(q, q0, q1);
@@ -1551,31 +1563,44 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
                     fb[2 * j + 1] = __float_as_uint(q1);
                 }
                 if (tdst) {
-                    uint4 pk;
+                    unsigned pk[CP];
+#pragma unroll
+                    for (int j = 0; j < CP; ++j) {
 #ifndef VG_OPERAND_BF16
-                    pk.x = pack_op(__uint_as_float(fb[0]), __uint_as_float(fb[1]));
-                    pk.y = pack_op(__uint_as_float(fb[2]), __uint_as_float(fb[3]));
-                    pk.z = pack_op(__uint_as_float(fb[4]), __uint_as_float(fb[5]));
-                    pk.w = pack_op(__uint_as_float(fb[6]), __uint_as_float(fb[7]));
+                        pk[j] = pack_op(__uint_as_float(fb[2 * j]), __uint_as_float(fb[2 * j + 1]));
 #else
-                    pk.x = __byte_perm(fb[0], fb[1], 0x7632);
-                    pk.y = __byte_perm(fb[2], fb[3], 0x7632);
-                    pk.z = __byte_perm(fb[4], fb[5], 0x7632);
-                    pk.w = __byte_perm(fb[6], fb[7], 0x7632);
+                        pk[j] = __byte_perm(fb[2 * j], fb[2 * j + 1], 0x7632);   // integers 0..255: high halves
 #endif
-                    *reinterpret_cast<uint4 *>(tdst + (oy >> 4) * (14 * 256) + (oy & 15) * 16) = pk;
+                    }
+                    op_t *dst = tdst + (oy >> 4) * (14 * 256) + (oy & 15) * 16;
+                    if (CW == 8) *reinterpret_cast<uint4 *>(dst) = make_uint4(pk[0], pk[1 % CP], pk[2 % CP], pk[3 % CP]);
+                    else if (CW == 4) *reinterpret_cast<uint2 *>(dst) = make_uint2(pk[0], pk[1 % CP]);
+                    else *reinterpret_cast<unsigned *>(dst) = pk[0];
                 }
                 if (u8) {
-                    unsigned lo = 0, hi = 0;
+                    uint8_t *dst = u8 + oy * S + ox0;
+                    unsigned w0 = 0, w1 = 0;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        lo |= ((unsigned)__uint_as_float(fb[j])) << (8 * j);
-                        hi |= ((unsigned)__uint_as_float(fb[4 + j])) << (8 * j);
+                    for (int j = 0; j < CW; ++j) {
+                        const unsigned byte = (unsigned)__uint_as_float(fb[j]);
+                        if (j < 4) w0 |= byte << (8 * j); else w1 |= byte << (8 * (j - 4));
                     }
-                    *reinterpret_cast<uint2 *>(u8 + oy * S + 8 * g) = make_uint2(lo, hi);
+                    if (CW == 8) *reinterpret_cast<uint2 *>(dst) = make_uint2(w0, w1);
+                    else if (CW == 4) *reinterpret_cast<unsigned *>(dst) = w0;
+                    else *reinterpret_cast<unsigned short *>(dst) = (unsigned short)w0;
                 }
                 ++oy;
             }
+        };
+        // two source rows per trip, the two row buffers swapping roles (no register copies)
+        hrow(ys, ha);
+        for (int y = ys;;) {
+            hrow(y + 1, hb);
+            emit_rows(y, ha, hb);
+            if (++y > ye) break;
+            hrow(y + 1, ha);
+            emit_rows(y, hb, ha);
+            if (++y > ye) break;
         }
         VG_TR(8);
     }
@@ -1590,13 +1615,13 @@ int launch_projection_t(VgHandle *h, const ProjParams &P, long long blocks, cuda
     return VG_OK;
 }
 
-template <int NTF, int MINB>
+template <int NTF, int MINB, int CW>
 int launch_fast_t(VgHandle *h, const ProjParams &P, long long blocks, cudaStream_t st)
 {
-    int rc = vg_set_smem_once(h, reinterpret_cast<const void *>(projection_fast_kernel<NTF, MINB>),
+    int rc = vg_set_smem_once(h, reinterpret_cast<const void *>(projection_fast_kernel<NTF, MINB, CW>),
                               sizeof(FastSmem));
     if (rc) return rc;
-    projection_fast_kernel<NTF, MINB><<<(unsigned)blocks, NTF, sizeof(FastSmem), st>>>(P);
+    projection_fast_kernel<NTF, MINB, CW><<<(unsigned)blocks, NTF, sizeof(FastSmem), st>>>(P);
     return VG_OK;
 }
 
@@ -1740,9 +1765,9 @@ int launch_projection(VgHandle *h, const float *d_points, const int32_t *d_offse
             VG_CUDA_CHECK(h, cudaMemsetAsync(P.defer, 0, sizeof(int32_t), st));
             P.block0 = (int32_t)b0;
             switch (h->sw.proj_variant) {
-            case 2: rc = launch_fast_t<256, 2>(h, P, nb, st); break;
-            case 3: rc = launch_fast_t<512, 2>(h, P, nb, st); break;
-            default: rc = launch_fast_t<256, 3>(h, P, nb, st); break;
+            case 2: rc = launch_fast_t<256, 3, 8>(h, P, nb, st); break;
+            case 3: rc = launch_fast_t<256, 3, 2>(h, P, nb, st); break;
+            default: rc = launch_fast_t<256, 3, 4>(h, P, nb, st); break;
             }
             if (rc) return rc;
             VG_LAUNCH_CHECK(h);
