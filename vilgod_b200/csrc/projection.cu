@@ -1048,7 +1048,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 #define VG_TR_ON(x)
 #endif
 
-template <int NTF, int MINB, int CW>
+template <int NTF, int MINB, int CW, int STAMP>
 __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjParams P)
 {
     constexpr int R = 112, Q = R - 2, NS = R / 4, MW = 4;
@@ -1361,13 +1361,24 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
             int *Bi = reinterpret_cast<int *>(sm.B) + orow * PW + ocol - 3 * PW - 3;
             const uint2 *cache = sm.cache + sm.base[d];
             if (xlo >= 3 && xhi <= Q - 2 && ylo >= 3 && yhi <= Q - 2) {      // no footprint leaves the image:
-                for (int p = tid; p < cnt; p += NTF) {                       // a thread stamps a whole footprint
-                    const uint2 e = cache[p];
-                    int *row = Bi + (int)(e.x >> 8) * PW + (int)(e.x & 255u);
+                if (STAMP == 1) {
+                    // one item = one column of a footprint: the five lanes of a point hit five consecutive banks
+                    for (int item = tid; item < 5 * cnt; item += NTF) {
+                        const int p = (item * 13108) >> 16, dx = item - 5 * p;     // item / 5 for item < 10,240
+                        const uint2 e = cache[p];
+                        int *col = Bi + (int)(e.x >> 8) * PW + (int)(e.x & 255u) + dx;
 #pragma unroll
-                    for (int dy = 0; dy < 5; ++dy)
+                        for (int dy = 0; dy < 5; ++dy) atomicMax(col + dy * PW, (int)e.y);
+                    }
+                } else {
+                    for (int p = tid; p < cnt; p += NTF) {                   // a thread stamps a whole footprint
+                        const uint2 e = cache[p];
+                        int *row = Bi + (int)(e.x >> 8) * PW + (int)(e.x & 255u);
 #pragma unroll
-                        for (int dx = 0; dx < 5; ++dx) atomicMax(row + dy * PW + dx, (int)e.y);
+                        for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+                            for (int dx = 0; dx < 5; ++dx) atomicMax(row + dy * PW + dx, (int)e.y);
+                    }
                 }
             } else {
                 for (int item = tid; item < 5 * cnt; item += NTF) {
@@ -1615,13 +1626,13 @@ int launch_projection_t(VgHandle *h, const ProjParams &P, long long blocks, cuda
     return VG_OK;
 }
 
-template <int NTF, int MINB, int CW>
+template <int NTF, int MINB, int CW, int STAMP>
 int launch_fast_t(VgHandle *h, const ProjParams &P, long long blocks, cudaStream_t st)
 {
-    int rc = vg_set_smem_once(h, reinterpret_cast<const void *>(projection_fast_kernel<NTF, MINB, CW>),
+    int rc = vg_set_smem_once(h, reinterpret_cast<const void *>(projection_fast_kernel<NTF, MINB, CW, STAMP>),
                               sizeof(FastSmem));
     if (rc) return rc;
-    projection_fast_kernel<NTF, MINB, CW><<<(unsigned)blocks, NTF, sizeof(FastSmem), st>>>(P);
+    projection_fast_kernel<NTF, MINB, CW, STAMP><<<(unsigned)blocks, NTF, sizeof(FastSmem), st>>>(P);
     return VG_OK;
 }
 
@@ -1765,9 +1776,9 @@ int launch_projection(VgHandle *h, const float *d_points, const int32_t *d_offse
             VG_CUDA_CHECK(h, cudaMemsetAsync(P.defer, 0, sizeof(int32_t), st));
             P.block0 = (int32_t)b0;
             switch (h->sw.proj_variant) {
-            case 2: rc = launch_fast_t<256, 3, 8>(h, P, nb, st); break;
-            case 3: rc = launch_fast_t<256, 3, 2>(h, P, nb, st); break;
-            default: rc = launch_fast_t<256, 3, 4>(h, P, nb, st); break;
+            case 2: rc = launch_fast_t<256, 3, 4, 0>(h, P, nb, st); break;
+            case 3: rc = launch_fast_t<256, 3, 8, 1>(h, P, nb, st); break;
+            default: rc = launch_fast_t<256, 3, 4, 1>(h, P, nb, st); break;
             }
             if (rc) return rc;
             VG_LAUNCH_CHECK(h);
