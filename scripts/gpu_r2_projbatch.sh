@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round 2: in-step projection time with the whole batch projected first (default) vs one chunk at a time.
 mkdir -p gpurun_out
-for pb in default 4096; do
+for pb in ${PBS:-default 4096}; do
   if [ $pb = default ]; then unset VG_PROJ_BATCH; else export VG_PROJ_BATCH=$pb; fi
   timeout 600 python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/bench_pb_$pb.json 2> gpurun_out/bench_pb_$pb.err
   echo "pb=$pb exit $?"; tail -2 gpurun_out/bench_pb_$pb.err

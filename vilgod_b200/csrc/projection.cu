@@ -88,7 +88,7 @@ struct ProjParams {
     float *dbg_dens;
     // fast path hand-over: images the fast kernel does not take (more than FAST_N points, or a touched
     // region beyond its shared-memory layout) are appended here and run by projection_kernel in list mode
-    int32_t *defer;        // [0] = count, [1 + i] = image index
+    int32_t *defer;        // [0] = count, [1] = cursor of the list-mode kernel, [2 + i] = image index
     int32_t block0;        // first image of this launch (fast kernel, launches above the list capacity)
     long long *trace;      // VG_PROJ_TRACE: clock64 stamps of thread 0 at the phase boundaries, [image][12]
     uint32_t bg_splat;     // two operand-typed background pixels when the whole background tile is one value
@@ -980,9 +980,15 @@ __global__ void __launch_bounds__(NT, R == 112 ? 2 : 1) projection_kernel(const 
         project_image<R>(P, (int)blockIdx.x, sm);
         return;
     }
+    // images are drawn from the list one at a time (they differ a lot in cost): defer[1] is the cursor
     const int count = P.defer[0];
-    for (int i = blockIdx.x; i < count; i += gridDim.x) {
-        project_image<R>(P, P.defer[1 + i], sm);
+    for (;;) {
+        if (threadIdx.x == 0) sm.spill_slot = atomicAdd(&P.defer[1], 1);
+        __syncthreads();
+        const int i = sm.spill_slot;
+        __syncthreads();       // everybody has the index before project_image reuses the field
+        if (i >= count) break;
+        project_image<R>(P, P.defer[2 + i], sm);
         __syncthreads();       // the next image re-initialises the shared state
     }
 }
@@ -1083,7 +1089,7 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
     const int n = P.offsets[c + 1] - beg;
     __syncthreads();
     auto hand_over = [&]() {
-        if (tid == 0) P.defer[1 + atomicAdd(P.defer, 1)] = b;
+        if (tid == 0) P.defer[2 + atomicAdd(P.defer, 1)] = b;
     };
     if (n > FAST_N) { hand_over(); return; }
     VG_TR(0);
@@ -1708,7 +1714,7 @@ int projection_init(VgHandle *h)
     }
 #endif
     // hand-over list of the fast kernel (count + image indices, 4 MB)
-    VG_CUDA_CHECK(h, cudaMalloc(&h->proj_defer, (size_t)(kDeferCap + 1) * sizeof(int32_t)));
+    VG_CUDA_CHECK(h, cudaMalloc(&h->proj_defer, (size_t)(kDeferCap + 2) * sizeof(int32_t)));
     // The fast kernel's shared-memory layout covers touched regions of F_MAXR rows x F_MAXS strips.
     // X, Y = clip(ceil(((u * obj_ratio + 1) / 2) * R), 1, R - 2) with |u| <= 1 up to a few ulps (1e-3 of
     // a cell covers them); the touched region adds 4 cells below and 2 above.  The kernel checks every
@@ -1773,7 +1779,7 @@ int launch_projection(VgHandle *h, const float *d_points, const int32_t *d_offse
         // general kernel in list mode, two CTAs per SM striding over the list
         for (long long b0 = 0; b0 < blocks; b0 += kDeferCap) {
             const long long nb = std::min(kDeferCap, blocks - b0);
-            VG_CUDA_CHECK(h, cudaMemsetAsync(P.defer, 0, sizeof(int32_t), st));
+            VG_CUDA_CHECK(h, cudaMemsetAsync(P.defer, 0, 2 * sizeof(int32_t), st));
             P.block0 = (int32_t)b0;
             switch (h->sw.proj_variant) {
             case 2: rc = launch_fast_t<256, 3, 4, 0>(h, P, nb, st); break;
