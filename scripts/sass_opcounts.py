@@ -8,7 +8,7 @@ import collections, re, subprocess, sys
 lib = sys.argv[1]
 txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
 OPS = ["UTCHMMA.2CTA", "UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAPF", "SYNCS", "MUFU.EX2",
-       "MUFU.TANH", "FFMA2", "ATOMS", "REDUX", "HMMA", "LDGSTS"]
+       "MUFU.TANH", "FFMA2", "ATOMS", "REDUX", "UBLKCP", "HMMA", "LDGSTS"]
 per = collections.OrderedDict()
 cur = None
 for ln in txt.splitlines():
@@ -40,4 +40,5 @@ for (k, c), name in zip(per.items(), demangle):
     tot.update(c)
 print(f"  {'ALL KERNELS':<100} " + " ".join(f"{tot[o]:>12}" for o in ["_total"] + OPS))
 print("# UTCHMMA* = tcgen05.mma, LDTM / STTM = tcgen05.ld / st, UTMALDG / UTMASTG = TMA tensor load / store,")
+print("# UBLKCP = cp.async.bulk (TMA without a tensor map: the projection's background stores),")
 print("# HMMA = legacy mma.sync (must be 0: no first-generation kernel ships)")
