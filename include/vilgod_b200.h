@@ -148,7 +148,10 @@ VG_API int vg_load_vit_weights(VgHandle *h, const VgVitWeights *w, void *stream)
 VG_API int vg_set_text_features(VgHandle *h, const float *d_text, int32_t P, const int32_t *class_map,
                          int32_t K, void *stream);
 
-/* bytes of scratch vg_encode_score / vg_classify need for up to max_images images per call */
+/* bytes of scratch vg_encode_score / vg_classify want for up to max_images images per call: the encoder
+ * buffers of one 4096-image chunk plus the tiles of the whole call (capped at 262,144 images = 26 GB),
+ * because vg_classify projects the whole batch before the tower walks over it.  A smaller workspace is
+ * accepted down to one chunk's worth (then the projection runs per chunk). */
 VG_API size_t vg_workspace_bytes(const VgHandle *h, int64_t max_images);
 
 /* Cluster canonicalisation for a packed frame: ego transform (nullable: d_transform = 16 doubles,
@@ -183,7 +186,8 @@ VG_API int vg_encode_score(VgHandle *h, const void *d_tiles, int64_t B, float *d
 VG_API int vg_vote(VgHandle *h, const float *d_probs, const int32_t *d_top1, int32_t C,
             int32_t *d_voted_class, float *d_voted_score, void *stream);
 
-/* project -> encode/score -> vote for C clusters, chunked internally to the workspace.
+/* project -> encode/score -> vote for C clusters: every cluster the workspace has tile room for is
+ * projected first (one launch), then the tower runs over the tiles in chunks of 4096 images.
  * Outputs as above; d_tiles scratch comes out of the workspace.
  *   d_u8_first [C,224,224] uint8 (nullable): the first view's image of every cluster, which the
  *   reference keeps as det.depth_image (zero_shot_detector.py:416-417, input_image_list[::V]). */
