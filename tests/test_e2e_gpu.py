@@ -430,3 +430,57 @@ def test_full_size_batch_properties(golden):
         assert torch.equal(pp["probs"], a["probs"][:n2])
     finally:
         e.close()
+
+
+def test_projection_batches_and_small_workspaces_give_the_same_bits(golden, monkeypatch):
+    """vg_classify projects as many clusters as the workspace has tile room for before the tower runs over
+    them in 4096-image chunks.  The schedule must not change a bit: the default (whole call in one
+    projection launch), VG_PROJ_BATCH = one chunk at a time, a batch that is not a multiple of the call, and
+    a caller-provided workspace that only holds 1.5 chunks of tiles (several projection batches, the last one
+    ragged) and a quarter of one chunk's workspace (smaller encoder chunks) all return identical results; a
+    workspace that cannot hold a single cluster is refused with VG_EWORKSPACE."""
+    import ctypes as C
+    from vilgod_b200 import _lib, synthetic, weights
+    from vilgod_b200.engine import Engine, _ptr, _stream
+    pts, off = synthetic.make_clusters(1100, n_min=10, n_max=600, seed=11)      # 11,000 images: 2.7 chunks
+    Cn, V = len(off) - 1, 10
+    sd, tf = weights.random_init_visual_state_dict(1234), weights.synthetic_text_features(24)
+
+    def run(env, ws_bytes=None):
+        for k in ("VG_PROJ_BATCH",):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        e = Engine(num_views=V)
+        try:
+            e.load_vit_weights(sd)
+            e.set_text_features(tf)
+            if ws_bytes is None:
+                out = e.classify(pts, off)
+            else:
+                p, o, _ = e._packed(pts, off)
+                out = e.alloc_outputs(Cn, want_feats=True)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+                rc = e.lib.vg_classify(e._h, _ptr(p), _ptr(o), Cn, _ptr(out["probs"]), _ptr(out["top1"]),
+                                       _ptr(out["feats"]), _ptr(out["voted_class"]), _ptr(out["voted_score"]),
+                                       _ptr(out["status"]), None, _ptr(ws), ws.numel(), _stream())
+                if rc != 0:
+                    return rc
+            torch.cuda.synchronize()
+            return {k: v.clone() for k, v in out.items() if v is not None}
+        finally:
+            e.close()
+
+    ref = run({})
+    assert int(ref["status"].abs().sum()) == 0
+    probe = Engine(num_views=V)
+    one_chunk = int(probe.lib.vg_workspace_bytes(probe._h, 4096))               # encoder buffers + 4096 tiles
+    probe.close()
+    tile = 196 * 256 * 2
+    cases = [run({"VG_PROJ_BATCH": "4096"}), run({"VG_PROJ_BATCH": "7000"}),
+             run({}, ws_bytes=one_chunk + 2048 * tile), run({}, ws_bytes=one_chunk // 4)]
+    for got in cases:
+        assert isinstance(got, dict)
+        for k in ("probs", "top1", "feats", "voted_class", "voted_score", "status"):
+            assert torch.equal(got[k], ref[k]), k
+    assert run({}, ws_bytes=1 << 20) == _lib.VG_EWORKSPACE
