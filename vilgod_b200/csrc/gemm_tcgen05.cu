@@ -75,14 +75,48 @@ struct Params {
     int32_t N, K;
 };
 
+// two packed fp32 (FFMA2 / FMUL2 / FADD2 on sm_100); each half is a correctly rounded IEEE operation
+using f32x2 = unsigned long long;
+__device__ __forceinline__ f32x2 pack2f(float a, float b)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2f(f32x2 v, float &a, float &b)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2f(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2f(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2f(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+// QuickGELU: x * sigmoid(1.702 x) with sigmoid(z) = 0.5 * tanh(z / 2) + 0.5: one MUFU op per element
+// (tanh.approx, relative error ~2^-11, below the rounding of the operand-typed output); the epilogue
+// evaluates it on packed pairs, this is the scalar form of the -DVG_EPI_SCALAR A/B build
+#ifdef VG_EPI_SCALAR
 __device__ __forceinline__ float quick_gelu(float v)
 {
-    // x * sigmoid(1.702 x) with sigmoid(z) = 0.5 * tanh(z / 2) + 0.5: one MUFU op per element
-    // (tanh.approx, relative error ~2^-11, below the bf16 rounding of the output)
     float t;
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * v));
     return v * fmaf(0.5f, t, 0.5f);
 }
+#endif
 // 16-byte chunk c of row r inside a 1024-byte-aligned SWIZZLE_128B slab
 __device__ __forceinline__ uint32_t slab_off(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
 // 16-byte chunk c (0..3) of the 64-byte row r inside a SWIZZLE_64B slab (32 rows x 32 operands, 2 KB)
@@ -437,6 +471,41 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                         const uint32_t *src = q < 4 ? &r0[8 * q] : &r1[8 * (q - 4)];
                         const float4 ba = __ldg(b4 + 2 * q), bb = __ldg(b4 + 2 * q + 1);
                         float v[8];
+#ifndef VG_EPI_SCALAR
+                        // packed fp32 pairs (FFMA2 / FMUL2: each half is an IEEE operation, same bits as the
+                        // scalar form): the LayerNorm fold is 2 and QuickGELU 2.5 instructions per PAIR
+                        // plus the two tanh, instead of 2 + 4 per element
+                        const float cv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+                        f32x2 pv[4];
+                        if (LNF) {
+                            const float4 sa = __ldg(s4 + 2 * q), sb = __ldg(s4 + 2 * q + 1);
+                            const float sv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+                            const f32x2 nmu2 = pack2f(nmu, nmu), rstd2 = pack2f(rstd, rstd);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                pv[j] = fma2f(rstd2, fma2f(nmu2, pack2f(sv[2 * j], sv[2 * j + 1]),
+                                                           pack2f(__uint_as_float(src[2 * j]), __uint_as_float(src[2 * j + 1]))),
+                                              pack2f(cv[2 * j], cv[2 * j + 1]));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                pv[j] = add2f(pack2f(__uint_as_float(src[2 * j]), __uint_as_float(src[2 * j + 1])),
+                                              pack2f(cv[2 * j], cv[2 * j + 1]));
+                        }
+                        if (EPI == VG_EPI_BIAS_QGELU_BF16) {
+                            const f32x2 k851 = pack2f(0.851f, 0.851f), khalf = pack2f(0.5f, 0.5f);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float a0, a1, t0, t1;
+                                unpack2f(mul2f(pv[j], k851), a0, a1);
+                                asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(a0));
+                                asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(a1));
+                                pv[j] = mul2f(pv[j], fma2f(khalf, pack2f(t0, t1), khalf));
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) unpack2f(pv[j], v[2 * j], v[2 * j + 1]);
+#else
                         if (LNF) {
                             const float4 sa = __ldg(s4 + 2 * q), sb = __ldg(s4 + 2 * q + 1);
                             const float sv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
@@ -454,6 +523,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
 #pragma unroll
                             for (int j = 0; j < 8; ++j) v[j] = quick_gelu(v[j]);
                         }
+#endif
                         *reinterpret_cast<uint4 *>(out + slab_off(lane, q)) =
                             make_uint4(pack_op(v[0], v[1]), pack_op(v[2], v[3]),
                                        pack_op(v[4], v[5]), pack_op(v[6], v[7]));
