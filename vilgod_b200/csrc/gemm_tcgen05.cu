@@ -105,6 +105,12 @@ __device__ __forceinline__ f32x2 add2f(f32x2 a, f32x2 b)
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+__device__ __forceinline__ f32x2 sub2f(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 
 // QuickGELU: x * sigmoid(1.702 x) with sigmoid(z) = 0.5 * tanh(z / 2) + 0.5: one MUFU op per element
 // (tanh.approx, relative error ~2^-11, below the rounding of the operand-typed output); the epilogue
@@ -303,6 +309,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                 ptx::mbar_wait(&tmem_full[as], aphase);
                 ptx::tc_fence_after();
                 float rs = 0.0f, rq = 0.0f;      // row sum / sum of squares of the new residual
+#ifndef VG_EPI_SCALAR
+                f32x2 rs2 = pack2f(0.0f, 0.0f), rq2 = rs2;   // ... accumulated per even / odd column
+#endif
                 unsigned char *hi_out = slab + 2 * SLAB_BYTES, *lo_out = slab + 3 * SLAB_BYTES;
 #pragma unroll 1
                 for (int c = 0; c < NCH; ++c) {
@@ -330,6 +339,22 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const float2 xh = unpack_op2(hw[j]), xl = unpack_op2(lw[j]);
+#ifndef VG_EPI_SCALAR
+                            // packed pairs: x_new = (hi + lo) + (acc + bias), statistics, new hi / lo split
+                            const f32x2 o = add2f(add2f(pack2f(xh.x, xh.y), pack2f(xl.x, xl.y)),
+                                                  add2f(pack2f(__uint_as_float(r[8 * q + 2 * j]),
+                                                               __uint_as_float(r[8 * q + 2 * j + 1])),
+                                                        pack2f(bv[2 * j], bv[2 * j + 1])));
+                            rs2 = add2f(rs2, o);
+                            rq2 = fma2f(o, o, rq2);
+                            float o0, o1;
+                            unpack2f(o, o0, o1);
+                            ho[j] = pack_op(o0, o1);
+                            const float2 nh = unpack_op2(ho[j]);
+                            float d0, d1;
+                            unpack2f(sub2f(o, pack2f(nh.x, nh.y)), d0, d1);
+                            lo[j] = pack_op(d0, d1);
+#else
                             const float o0 = (xh.x + xl.x) + (__uint_as_float(r[8 * q + 2 * j]) + bv[2 * j]);
                             const float o1 = (xh.y + xl.y) + (__uint_as_float(r[8 * q + 2 * j + 1]) + bv[2 * j + 1]);
                             rs += o0 + o1;
@@ -337,6 +362,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                             ho[j] = pack_op(o0, o1);
                             const float2 nh = unpack_op2(ho[j]);
                             lo[j] = pack_op(o0 - nh.x, o1 - nh.y);
+#endif
                         }
                         const uint32_t oo = slab_off(lane, ib * 4 + q);
                         *reinterpret_cast<uint4 *>(hi_out + oo) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
@@ -353,6 +379,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                         }
                     }
                 }
+#ifndef VG_EPI_SCALAR
+                {
+                    float a, b;
+                    unpack2f(rs2, a, b);
+                    rs = a + b;
+                    unpack2f(rq2, a, b);
+                    rq = a + b;
+                }
+#endif
                 if (WIDE) {     // the column-half partner's partial sums, added in fixed order
                     float2 *xs = reinterpret_cast<float2 *>(xstat) + lane_base + lane;
                     if (chalf == 1) *xs = make_float2(rs, rq);
