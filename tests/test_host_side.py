@@ -155,3 +155,35 @@ def test_prompt_encoding_through_the_callers_clip_package(golden, tmp_path):
     from oracle.make_golden import weights_fingerprint
     sha, _ = weights_fingerprint({k: v.float() for k, v in model.visual.state_dict().items()})
     assert sha == str(golden["vit"]["plain_weights_sha256"])
+
+
+def test_fast_projection_kernel_closed_forms():
+    """The fast projection kernel (csrc/projection.cu: projection_fast_kernel) derives the output rows /
+    8-pixel column groups that can differ from background in closed form instead of scanning the bilinear
+    table: it relies on (1) the align_corners source index of torch's area_pixel_compute_source_index,
+    computed in fp32 as floor(fl(fl((Q-1)/(S-1)) * o)), being equal to the integer floor(o (Q-1) / (S-1)) for
+    every output index (projection_init re-checks this on the device table and falls back to the general
+    kernel otherwise), and (2) first_with(t) = ceil(t (S-1) / (Q-1)) being the first output index whose
+    source index reaches t.  Both are checked here exhaustively, for R = 112 and R = 224, against the
+    definition the general kernel uses (a row is active when one of its two source rows lies in [lo, hi])."""
+    f = np.float32
+    S, NG = 224, 28
+    for R in (112, 224):
+        Q = R - 2
+        scale = f(f(Q - 1) / f(S - 1))
+        i0 = np.array([min(int(np.floor(f(scale * f(o)))), Q - 1) for o in range(S)])
+        assert np.array_equal(i0, (np.arange(S) * (Q - 1)) // (S - 1))
+
+        def first_with(t):
+            return 0 if t <= 0 else (t * (S - 1) + (Q - 2)) // (Q - 1)
+
+        y1 = i0 + (i0 < Q - 1)
+        g = np.arange(NG)
+        xa, xb = i0[8 * g], i0[8 * g + 7] + (i0[8 * g + 7] < Q - 1)
+        for lo in range(Q):
+            for hi in range(lo, Q, 3 if R == 224 else 1):
+                rows = np.flatnonzero(~((y1 < lo) | (i0 > hi)))
+                assert (rows.min(), rows.max()) == (first_with(lo - 1), min(first_with(hi + 1) - 1, S - 1))
+                cols = np.flatnonzero(~((xb < lo) | (xa > hi)))
+                assert (cols.min(), cols.max()) == (first_with(lo - 1) >> 3,
+                                                    min(min(first_with(hi + 1) - 1, S - 1) >> 3, NG - 1))
