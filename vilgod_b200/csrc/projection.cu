@@ -88,7 +88,8 @@ struct ProjParams {
     float *dbg_dens;
     // fast path hand-over: images the fast kernel does not take (more than FAST_N points, or a touched
     // region beyond its shared-memory layout) are appended here and run by projection_kernel in list mode
-    int32_t *defer;        // [0] = count, [1] = cursor of the list-mode kernel, [2 + i] = image index
+    int32_t *defer;        // [0] = count, [1] = cursor of the list-mode kernel, [2] = image counter of the
+                           // fast kernel's persistent CTAs, [3 + i] = image index
     int32_t block0;        // first image of this launch (fast kernel, launches above the list capacity)
     long long *trace;      // VG_PROJ_TRACE: clock64 stamps of thread 0 at the phase boundaries, [image][12]
     uint32_t bg_splat;     // two operand-typed background pixels when the whole background tile is one value
@@ -988,7 +989,7 @@ __global__ void __launch_bounds__(NT, R == 112 ? 2 : 1) projection_kernel(const 
         const int i = sm.spill_slot;
         __syncthreads();       // everybody has the index before project_image reuses the field
         if (i >= count) break;
-        project_image<R>(P, P.defer[2 + i], sm);
+        project_image<R>(P, P.defer[3 + i], sm);
         __syncthreads();       // the next image re-initialises the shared state
     }
 }
@@ -1025,6 +1026,7 @@ struct FastSmem {
     int ulo, uhi, vlo, vhi;
     float red[32];
     int degenerate;
+    int next;              // next image of this CTA (persistent loop)
     uint4 bgsrc[448];      // one patch row (14 patches x 512 B) of background pixels: source of the bulk stores
     float2 lw[S];          // bilinear weights (l0, l1) of output row / column i ...
     unsigned char i0[S];   // ... and its first source row / column (copy of ProjTables, filled per CTA)
@@ -1054,28 +1056,19 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 #define VG_TR_ON(x)
 #endif
 
-template <int NTF, int MINB, int CW, int STAMP>
-__global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjParams P)
+// one image (cluster b / V, view b % V); the bilinear table and the constant background row in `sm` were
+// filled by the kernel before its image loop
+template <int NTF, int CW, int STAMP>
+__device__ __forceinline__ void fast_image(const ProjParams &P, const int b, FastSmem &sm)
 {
     constexpr int R = 112, Q = R - 2, NS = R / 4, MW = 4;
     constexpr int NWF = NTF / 32;
     constexpr int KQ = ((F_MAXR / 2) * F_MAXS + NTF - 1) / NTF;         // (row pair, strip) items per thread
     constexpr int PW = 4 * F_PITCH;                                     // buffer pitch in floats
-    static_assert(NTF >= S && NTF >= 64, "setup roles are mapped to thread ids");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    FastSmem &sm = *reinterpret_cast<FastSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = P.block0 + (int)blockIdx.x;
     const int c = b / P.V, v = b - c * P.V;
     // shared state first, and ONE early barrier (every warp reaches it at once) instead of one between
-    // the reduction's initial values and its atomics; the bilinear table is requested now and stored
-    // once the points are through
-    float2 t_lw = make_float2(0.f, 0.f);
-    int t_i0 = 0;
-    if (tid < S) {
-        t_lw = make_float2(__ldg(&P.tab->l0[tid]), __ldg(&P.tab->l1[tid]));
-        t_i0 = __ldg(&P.tab->i0[tid]);
-    }
+    // the reduction's initial values and its atomics
     if (tid < 6) sm.ext[tid] = tid < 3 ? 0u : 0xffffffffu;
     if (tid < D * MW) { (&sm.rowmask[0][0])[tid] = 0u; (&sm.colmask[0][0])[tid] = 0u; }
     if (tid < D) sm.cnt[tid] = 0;
@@ -1083,13 +1076,11 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
         sm.degenerate = 0;
         sm.ulo = Q; sm.uhi = -1; sm.vlo = Q; sm.vhi = -1;
     }
-    if (P.bg_splat != 0u && P.tiles)
-        for (int i = tid; i < 448; i += NTF) sm.bgsrc[i] = make_uint4(P.bg_splat, P.bg_splat, P.bg_splat, P.bg_splat);
     const int beg = P.offsets[c];
     const int n = P.offsets[c + 1] - beg;
     __syncthreads();
     auto hand_over = [&]() {
-        if (tid == 0) P.defer[2 + atomicAdd(P.defer, 1)] = b;
+        if (tid == 0) P.defer[3 + atomicAdd(P.defer, 1)] = b;
     };
     if (n > FAST_N) { hand_over(); return; }
     VG_TR(0);
@@ -1128,10 +1119,6 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
             atomicMax(&sm.ext[0], k0); atomicMax(&sm.ext[1], k1); atomicMax(&sm.ext[2], k2);
             atomicMin(&sm.ext[3], k3); atomicMin(&sm.ext[4], k4); atomicMin(&sm.ext[5], k5);
             if (!all_finite) sm.degenerate = 1;
-        }
-        if (tid < S) {
-            sm.lw[tid] = t_lw;
-            sm.i0[tid] = (unsigned char)t_i0;
         }
         __syncthreads();
     }
@@ -1623,6 +1610,31 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
     }
 }
 
+// Persistent CTAs (three per SM): the bilinear table and the constant background row are set up once,
+// then images are drawn from a counter (they differ a lot in cost); the next index is fetched before the
+// barrier that ends an image, so the loop adds one barrier per image and no exposed latency.
+template <int NTF, int MINB, int CW, int STAMP>
+__global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjParams P, const int images)
+{
+    static_assert(NTF >= S && NTF >= 64, "setup roles are mapped to thread ids");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FastSmem &sm = *reinterpret_cast<FastSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+    if (tid < S) {
+        sm.lw[tid] = make_float2(__ldg(&P.tab->l0[tid]), __ldg(&P.tab->l1[tid]));
+        sm.i0[tid] = (unsigned char)__ldg(&P.tab->i0[tid]);
+    }
+    if (P.bg_splat != 0u && P.tiles)
+        for (int i = tid; i < 448; i += NTF) sm.bgsrc[i] = make_uint4(P.bg_splat, P.bg_splat, P.bg_splat, P.bg_splat);
+    int i = (int)blockIdx.x;
+    while (i < images) {
+        fast_image<NTF, CW, STAMP>(P, P.block0 + i, sm);
+        if (tid == 0) sm.next = (int)gridDim.x + atomicAdd(&P.defer[2], 1);
+        __syncthreads();       // the image is finished by every warp; the next one re-initialises `sm`
+        i = sm.next;
+    }
+}
+
 template <int R, bool LIST>
 int launch_projection_t(VgHandle *h, const ProjParams &P, long long blocks, cudaStream_t st)
 {
@@ -1638,7 +1650,8 @@ int launch_fast_t(VgHandle *h, const ProjParams &P, long long blocks, cudaStream
     int rc = vg_set_smem_once(h, reinterpret_cast<const void *>(projection_fast_kernel<NTF, MINB, CW, STAMP>),
                               sizeof(FastSmem));
     if (rc) return rc;
-    projection_fast_kernel<NTF, MINB, CW, STAMP><<<(unsigned)blocks, NTF, sizeof(FastSmem), st>>>(P);
+    const long long grid = std::min<long long>(blocks, (long long)MINB * h->num_sms);
+    projection_fast_kernel<NTF, MINB, CW, STAMP><<<(unsigned)grid, NTF, sizeof(FastSmem), st>>>(P, (int)blocks);
     return VG_OK;
 }
 
@@ -1714,7 +1727,7 @@ int projection_init(VgHandle *h)
     }
 #endif
     // hand-over list of the fast kernel (count + image indices, 4 MB)
-    VG_CUDA_CHECK(h, cudaMalloc(&h->proj_defer, (size_t)(kDeferCap + 2) * sizeof(int32_t)));
+    VG_CUDA_CHECK(h, cudaMalloc(&h->proj_defer, (size_t)(kDeferCap + 3) * sizeof(int32_t)));
     // The fast kernel's shared-memory layout covers touched regions of F_MAXR rows x F_MAXS strips.
     // X, Y = clip(ceil(((u * obj_ratio + 1) / 2) * R), 1, R - 2) with |u| <= 1 up to a few ulps (1e-3 of
     // a cell covers them); the touched region adds 4 cells below and 2 above.  The kernel checks every
@@ -1779,7 +1792,7 @@ int launch_projection(VgHandle *h, const float *d_points, const int32_t *d_offse
         // general kernel in list mode, two CTAs per SM striding over the list
         for (long long b0 = 0; b0 < blocks; b0 += kDeferCap) {
             const long long nb = std::min(kDeferCap, blocks - b0);
-            VG_CUDA_CHECK(h, cudaMemsetAsync(P.defer, 0, 2 * sizeof(int32_t), st));
+            VG_CUDA_CHECK(h, cudaMemsetAsync(P.defer, 0, 3 * sizeof(int32_t), st));
             P.block0 = (int32_t)b0;
             switch (h->sw.proj_variant) {
             case 2: rc = launch_fast_t<256, 3, 4, 0>(h, P, nb, st); break;
