@@ -206,6 +206,18 @@ def test_fast_and_general_kernels_agree(monkeypatch):
     assert np.array_equal(outs["1"]["densified"].cpu().numpy().reshape(C, V, 110, 110)[ok], dens_o)
     assert np.array_equal(outs["1"]["u8"].cpu().numpy().reshape(C, V, 224, 224)[ok], u8_o)
     assert torch.equal(tiles_to_u8(outs["1"]["tiles"]), outs["1"]["u8"])
+    # R = 224 (BASELINE configs[3]): the fast kernel's 512-thread instantiation against the general kernel
+    r224 = {}
+    for variant in ("0", "1"):
+        monkeypatch.setenv("VG_PROJ_VARIANT", variant)
+        eng = Engine(num_views=6, resolution=224)
+        try:
+            r224[variant] = eng.project(pts, off, want_u8=True, want_densified=True)
+        finally:
+            eng.close()
+    assert torch.equal(r224["1"]["status"], r224["0"]["status"])
+    assert torch.equal(r224["1"]["tiles"], r224["0"]["tiles"]) and torch.equal(r224["1"]["u8"], r224["0"]["u8"])
+    assert torch.equal(r224["1"]["densified"].reshape(C, -1)[okt], r224["0"]["densified"].reshape(C, -1)[okt])
 
 
 def test_r224_grid_against_reference_and_oracle(golden, engines):

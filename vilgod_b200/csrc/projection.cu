@@ -572,13 +572,16 @@ __device__ __forceinline__ void project_image(const ProjParams &P, const int b, 
         const int ky = lane >> 1, half = lane & 1;
         const int py_lo = (oy_lo - ky + 15) >> 4, py_hi = (oy_hi - ky) >> 4;     // arithmetic shifts: floor
         const int px_lo = (g_lo - half + 1) >> 1, px_hi = (g_hi - half) >> 1;
+        const bool splat = P.bg_splat != 0u;     // the background is one value (R = 112, 224): nothing to load
         if (tile) {
             const uint4 *__restrict__ src = tab->bg_tile + lane;
             uint4 *dst = reinterpret_cast<uint4 *>(tile) + lane;
+            const uint4 bgv = make_uint4(P.bg_splat, P.bg_splat, P.bg_splat, P.bg_splat);
             int py = warp >= 14 ? 1 : 0, px = warp >= 14 ? warp - 14 : warp;
 #pragma unroll 13
             for (int p = warp; p < 196; p += NW) {
-                if (py < py_lo || py > py_hi || px < px_lo || px > px_hi) dst[p * 32] = __ldg(src + p * 32);
+                if (py < py_lo || py > py_hi || px < px_lo || px > px_hi)
+                    dst[p * 32] = splat ? bgv : __ldg(src + p * 32);
                 px += 2; py += 1;
                 if (px >= 14) { px -= 14; py += 1; }
             }
@@ -588,7 +591,8 @@ __device__ __forceinline__ void project_image(const ProjParams &P, const int b, 
             for (int p = warp; p < 196; p += NW) {
                 const int oy = py * 16 + ky, g = px * 2 + half;
                 if (py < py_lo || py > py_hi || px < px_lo || px > px_hi)
-                    *reinterpret_cast<uint2 *>(u8 + oy * S + 8 * g) = __ldg(&tab->bg_u8[(oy * S + 8 * g) >> 3]);
+                    *reinterpret_cast<uint2 *>(u8 + oy * S + 8 * g) =
+                        splat ? make_uint2(P.bg_u8_splat, P.bg_u8_splat) : __ldg(&tab->bg_u8[(oy * S + 8 * g) >> 3]);
                 px += 2; py += 1;
                 if (px >= 14) { px -= 14; py += 1; }
             }
@@ -1013,15 +1017,20 @@ __global__ void __launch_bounds__(NT, R == 112 ? 2 : 1) projection_kernel(const 
 //     horizontally interpolated source rows y0 / y0 + 1 in registers and advances them as the run
 //     moves down -- no intermediate buffer, no barrier, every horizontal interpolation done ~once.
 constexpr int FAST_N = 2048;
-constexpr int F_MAXR = 96, F_MAXS = 24;
-constexpr int F_PITCH = F_MAXS + 5;      // float4 strips per buffer row: two halo strips per side, odd
-constexpr int F_BROWS = F_MAXR + 3;      // halo row below / above + the second row of an odd last pair
+// largest touched region the path takes (rows x float4 strips) and its buffer.  R = 112: 96 x 24 (63 KB per
+// CTA, three 256-thread CTAs per SM).  R = 224 (BASELINE configs[3]): 186 x 48 (X, Y in [23, 202]), 187 KB:
+// one 512-thread CTA per SM with nine (row pair, strip) items per thread in its 128 registers.
+template <int R> struct FastGeo {
+    static constexpr int MAXR = R == 112 ? 96 : 186, MAXS = R == 112 ? 24 : 48;
+    static constexpr int PITCH = MAXS + 5;     // float4 strips per buffer row: two halo strips per side, odd
+    static constexpr int BROWS = MAXR + 3;     // halo row below / above + the second row of an odd last pair
+};
 
-struct FastSmem {
-    float4 B[F_BROWS * F_PITCH];
+template <int R> struct FastSmem {
+    float4 B[FastGeo<R>::BROWS * FastGeo<R>::PITCH];
     uint2 cache[FAST_N];   // per point, sorted by depth slice: (x | y << 8, value bits)
     unsigned ext[6];
-    unsigned rowmask[D][4], colmask[D][4];
+    unsigned rowmask[D][(R + 31) / 32], colmask[D][(R + 31) / 32];   // occupied grid rows / columns per slice
     int ylo[D], yhi[D], xlo[D], xhi[D], cnt[D], base[D];
     int ulo, uhi, vlo, vhi;
     float red[32];
@@ -1058,10 +1067,11 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 // one image (cluster b / V, view b % V); the bilinear table and the constant background row in `sm` were
 // filled by the kernel before its image loop
-template <int NTF, int CW, int STAMP>
-__device__ __forceinline__ void fast_image(const ProjParams &P, const int b, FastSmem &sm)
+template <int R, int NTF, int CW, int STAMP>
+__device__ __forceinline__ void fast_image(const ProjParams &P, const int b, FastSmem<R> &sm)
 {
-    constexpr int R = 112, Q = R - 2, NS = R / 4, MW = 4;
+    constexpr int Q = R - 2, NS = R / 4, MW = (R + 31) / 32;
+    constexpr int F_MAXR = FastGeo<R>::MAXR, F_MAXS = FastGeo<R>::MAXS, F_PITCH = FastGeo<R>::PITCH;
     constexpr int NWF = NTF / 32;
     constexpr int KQ = ((F_MAXR / 2) * F_MAXS + NTF - 1) / NTF;         // (row pair, strip) items per thread
     constexpr int PW = 4 * F_PITCH;                                     // buffer pitch in floats
@@ -1342,9 +1352,15 @@ __device__ __forceinline__ void fast_image(const ProjParams &P, const int b, Fas
         // the normalised image overwrites it)
         {
             const int r_lo = max(max(ylo - 4, 0) + orow - 2, 0), r_hi = min(min(yhi + 2, Q - 1) + orow + 2, nr + 2);
-            if (lane < ns + 3)
+            if (F_PITCH <= 32) {        // a lane per strip
+                if (lane < ns + 3)
+                    for (int r = r_lo + warp; r <= r_hi; r += NWF)
+                        sm.B[r * F_PITCH + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
                 for (int r = r_lo + warp; r <= r_hi; r += NWF)
-                    sm.B[r * F_PITCH + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int sb = lane; sb < ns + 3; sb += 32)
+                        sm.B[r * F_PITCH + sb] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
         __syncthreads();
         VG_TR_ON(if (P.trace) { const long long t = clock64(); tr_clear += t - tr_t; tr_t = t; })
@@ -1467,10 +1483,18 @@ __device__ __forceinline__ void fast_image(const ProjParams &P, const int b, Fas
             return t;
         };
         const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (lane < F_PITCH) {
-            const bool edge = lane < 2 || lane >= ns + 2;
-            for (int rb = warp; rb < nr + 3; rb += NWF)
-                if (edge || rb == 0 || rb > nr) sm.B[rb * F_PITCH + lane] = one4;
+        if (F_PITCH <= 32) {            // a lane per strip
+            if (lane < F_PITCH) {
+                const bool edge = lane < 2 || lane >= ns + 2;
+                for (int rb = warp; rb < nr + 3; rb += NWF)
+                    if (edge || rb == 0 || rb > nr) sm.B[rb * F_PITCH + lane] = one4;
+            }
+        } else {
+            for (int sb = lane; sb < F_PITCH; sb += 32) {
+                const bool edge = sb < 2 || sb >= ns + 2;
+                for (int rb = warp; rb < nr + 3; rb += NWF)
+                    if (edge || rb == 0 || rb > nr) sm.B[rb * F_PITCH + sb] = one4;
+            }
         }
 #pragma unroll
         for (int k = 0; k < KQ; ++k) {
@@ -1613,12 +1637,12 @@ __device__ __forceinline__ void fast_image(const ProjParams &P, const int b, Fas
 // Persistent CTAs (three per SM): the bilinear table and the constant background row are set up once,
 // then images are drawn from a counter (they differ a lot in cost); the next index is fetched before the
 // barrier that ends an image, so the loop adds one barrier per image and no exposed latency.
-template <int NTF, int MINB, int CW, int STAMP>
+template <int R, int NTF, int MINB, int CW, int STAMP>
 __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjParams P, const int images)
 {
     static_assert(NTF >= S && NTF >= 64, "setup roles are mapped to thread ids");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    FastSmem &sm = *reinterpret_cast<FastSmem *>(smem_raw);
+    FastSmem<R> &sm = *reinterpret_cast<FastSmem<R> *>(smem_raw);
     const int tid = threadIdx.x;
     if (tid < S) {
         sm.lw[tid] = make_float2(__ldg(&P.tab->l0[tid]), __ldg(&P.tab->l1[tid]));
@@ -1628,7 +1652,7 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
         for (int i = tid; i < 448; i += NTF) sm.bgsrc[i] = make_uint4(P.bg_splat, P.bg_splat, P.bg_splat, P.bg_splat);
     int i = (int)blockIdx.x;
     while (i < images) {
-        fast_image<NTF, CW, STAMP>(P, P.block0 + i, sm);
+        fast_image<R, NTF, CW, STAMP>(P, P.block0 + i, sm);
         if (tid == 0) sm.next = (int)gridDim.x + atomicAdd(&P.defer[2], 1);
         __syncthreads();       // the image is finished by every warp; the next one re-initialises `sm`
         i = sm.next;
@@ -1644,14 +1668,14 @@ int launch_projection_t(VgHandle *h, const ProjParams &P, long long blocks, cuda
     return VG_OK;
 }
 
-template <int NTF, int MINB, int CW, int STAMP>
+template <int R, int NTF, int MINB, int CW, int STAMP>
 int launch_fast_t(VgHandle *h, const ProjParams &P, long long blocks, cudaStream_t st)
 {
-    int rc = vg_set_smem_once(h, reinterpret_cast<const void *>(projection_fast_kernel<NTF, MINB, CW, STAMP>),
-                              sizeof(FastSmem));
+    int rc = vg_set_smem_once(h, reinterpret_cast<const void *>(projection_fast_kernel<R, NTF, MINB, CW, STAMP>),
+                              sizeof(FastSmem<R>));
     if (rc) return rc;
     const long long grid = std::min<long long>(blocks, (long long)MINB * h->num_sms);
-    projection_fast_kernel<NTF, MINB, CW, STAMP><<<(unsigned)grid, NTF, sizeof(FastSmem), st>>>(P, (int)blocks);
+    projection_fast_kernel<R, NTF, MINB, CW, STAMP><<<(unsigned)grid, NTF, sizeof(FastSmem<R>), st>>>(P, (int)blocks);
     return VG_OK;
 }
 
@@ -1738,7 +1762,9 @@ int projection_init(VgHandle *h)
         const int hi = (int)std::min((double)(R - 2), std::ceil((1.0 + rho) * 0.5 * R + 1e-3));
         const int rows = std::min(hi + 2, Q - 1) - std::max(lo - 4, 0) + 1;
         const int strips = (std::min(hi + 2, Q - 1) >> 2) - (std::max(lo - 4, 0) >> 2) + 1;
-        h->proj_fast = R == 112 && rows <= F_MAXR && strips <= F_MAXS && h->proj_table_exact;
+        const int max_rows = R == 112 ? FastGeo<112>::MAXR : FastGeo<224>::MAXR;
+        const int max_strips = R == 112 ? FastGeo<112>::MAXS : FastGeo<224>::MAXS;
+        h->proj_fast = rows <= max_rows && strips <= max_strips && h->proj_table_exact;
     }
     VG_CUDA_CHECK(h, cudaDeviceSynchronize());
     return VG_OK;
@@ -1794,14 +1820,21 @@ int launch_projection(VgHandle *h, const float *d_points, const int32_t *d_offse
             const long long nb = std::min(kDeferCap, blocks - b0);
             VG_CUDA_CHECK(h, cudaMemsetAsync(P.defer, 0, 3 * sizeof(int32_t), st));
             P.block0 = (int32_t)b0;
-            switch (h->sw.proj_variant) {
-            case 2: rc = launch_fast_t<256, 3, 4, 0>(h, P, nb, st); break;
-            case 3: rc = launch_fast_t<256, 3, 8, 1>(h, P, nb, st); break;
-            default: rc = launch_fast_t<256, 3, 4, 1>(h, P, nb, st); break;
+            if (cfg.resolution == 224) {
+                rc = launch_fast_t<224, 512, 1, 4, 1>(h, P, nb, st);
+            } else {
+                switch (h->sw.proj_variant) {
+                case 2: rc = launch_fast_t<112, 256, 3, 4, 0>(h, P, nb, st); break;
+                case 3: rc = launch_fast_t<112, 256, 3, 8, 1>(h, P, nb, st); break;
+                default: rc = launch_fast_t<112, 256, 3, 4, 1>(h, P, nb, st); break;
+                }
             }
             if (rc) return rc;
             VG_LAUNCH_CHECK(h);
-            if ((rc = launch_projection_t<112, true>(h, P, std::min<long long>(nb, 2ll * h->num_sms), st))) return rc;
+            rc = cfg.resolution == 224
+                     ? launch_projection_t<224, true>(h, P, std::min<long long>(nb, (long long)h->num_sms), st)
+                     : launch_projection_t<112, true>(h, P, std::min<long long>(nb, 2ll * h->num_sms), st);
+            if (rc) return rc;
             VG_LAUNCH_CHECK(h);
         }
         if (P.trace) print_trace(h, (int)std::min<long long>(blocks, kTraceImages), st);
