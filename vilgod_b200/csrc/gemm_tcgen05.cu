@@ -309,9 +309,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                 ptx::mbar_wait(&tmem_full[as], aphase);
                 ptx::tc_fence_after();
                 float rs = 0.0f, rq = 0.0f;      // row sum / sum of squares of the new residual
-#ifndef VG_EPI_SCALAR
-                f32x2 rs2 = pack2f(0.0f, 0.0f), rq2 = rs2;   // ... accumulated per even / odd column
-#endif
                 unsigned char *hi_out = slab + 2 * SLAB_BYTES, *lo_out = slab + 3 * SLAB_BYTES;
 #pragma unroll 1
                 for (int c = 0; c < NCH; ++c) {
@@ -345,10 +342,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                                                   add2f(pack2f(__uint_as_float(r[8 * q + 2 * j]),
                                                                __uint_as_float(r[8 * q + 2 * j + 1])),
                                                         pack2f(bv[2 * j], bv[2 * j + 1])));
-                            rs2 = add2f(rs2, o);
-                            rq2 = fma2f(o, o, rq2);
                             float o0, o1;
                             unpack2f(o, o0, o1);
+                            rs += o0 + o1;                 // the statistics keep their scalar summation order:
+                            rq += o0 * o0 + o1 * o1;       // same LayerNorm bits as the scalar epilogue
                             ho[j] = pack_op(o0, o1);
                             const float2 nh = unpack_op2(ho[j]);
                             float d0, d1;
@@ -379,15 +376,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                         }
                     }
                 }
-#ifndef VG_EPI_SCALAR
-                {
-                    float a, b;
-                    unpack2f(rs2, a, b);
-                    rs = a + b;
-                    unpack2f(rq2, a, b);
-                    rq = a + b;
-                }
-#endif
                 if (WIDE) {     // the column-half partner's partial sums, added in fixed order
                     float2 *xs = reinterpret_cast<float2 *>(xstat) + lane_base + lane;
                     if (chalf == 1) *xs = make_float2(rs, rq);
