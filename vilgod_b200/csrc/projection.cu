@@ -1,4 +1,4 @@
-// Multi-view depth projection of packed ragged point clusters -- one fused sm_100a kernel.
+// Multi-view depth projection of packed ragged point clusters -- fused sm_100a kernels (one image per CTA pass).
 //
 // Replaces, for one (cluster, view) per CTA, everything between the canonicalised cluster and the
 // CLIP patch embedding in the reference:
@@ -16,21 +16,26 @@
 // memory, and the only HBM writes are the patch-major tile (100,352 B per image) and, on request,
 // the uint8 image.  Algorithmic bytes per cluster: 12 N + V * 224*224*2.
 //
-// Two ways through the per-slice stencil, chosen per image, identical results:
-//   stamp  (N <= 1024, 87 % of a Waymo-shaped mix): the quantised points are counting-sorted by depth
-//          slice; per occupied slice the 5x5 max-pool is applied AT SCATTER TIME (each point stamps its
-//          5x5 footprint with shared-memory atomicMax: max-pool of a sparse grid is the union of the
-//          footprints), and the 3x3 Gaussian + depth max run only over the slice's bounding box with
-//          the work flattened over all lanes.  Nothing outside the bounding box is touched.
-//   dense  (larger clusters, and whenever the raw grid is requested as a debug tap): scatter-max of
-//          the raw cells, then a row-streaming separable 5x5 max + Gaussian with register rings.
+// Two kernels, bit-identical results:
+//   projection_fast_kernel  clusters up to 2048 points (every cluster of a Waymo-shaped frame) whose touched
+//          region fits its bounding-box buffer (always at the reference's obj_ratio): persistent CTAs, the
+//          running depth-max image in registers, stamped max-pool, band-limited Gaussian, background as bulk
+//          stores from a constant patch row, walking bilinear emit.  R = 112: three 256-thread CTAs per SM;
+//          R = 224: one 512-thread CTA per SM.  What it does not take goes onto a device-side list ...
+//   projection_kernel       ... which the general kernel works off (list mode); it also serves other
+//          obj_ratios and the raw-grid debug tap (one CTA per image).  Two ways through its per-slice stencil:
+//     stamp  (N <= 1024): the quantised points are counting-sorted by depth slice; per occupied slice the
+//            5x5 max-pool is applied AT SCATTER TIME (each point stamps its 5x5 footprint with
+//            shared-memory atomicMax: max-pool of a sparse grid is the union of the footprints), and the
+//            3x3 Gaussian + depth max run only over the slice's bounding box.
+//     dense  (larger clusters, and whenever the raw grid is requested): scatter-max of the raw cells, then
+//            a row-streaming separable 5x5 max + Gaussian with register rings.
 // The emit (bilinear, uint8 quantisation, patch-major tile) is restricted to the output rows AND
-// column groups whose four source pixels can differ from background; everything else is copied from
-// a precomputed background tile.
+// column groups whose four source pixels can differ from background; everything else is the background
+// value (one constant at R = 112 / 224, else copied from a precomputed tile).
 //
-// R = 112 (reference configuration): grid slice + image in shared memory, two CTAs per SM.
-// R = 224 (BASELINE.json configs[3] sweep): the slice alone is 196 KB, so the running image lives
-// in a per-SM scratch in global memory (L2 resident) and one CTA runs per SM.
+// General kernel: R = 112: grid slice + image in shared memory, two CTAs per SM.  R = 224: the slice alone
+// is 196 KB, so the running image lives in a per-SM scratch in global memory (L2 resident), one CTA per SM.
 //
 // Numerics contract (tests/test_projection_gpu.py): occupancy masks and scatter winners bit-exact
 // against the oracle; every fp32 operation up to the scatter is a single IEEE-rounded operation in
