@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--clusters-per-frame", type=int, default=300)
     ap.add_argument("--views", type=int, default=10)
     ap.add_argument("--n-max", type=int, default=2048)
-    ap.add_argument("--cpu-sample-clusters", type=int, default=32,
+    ap.add_argument("--cpu-sample-clusters", type=int, default=48,
                     help="clusters of the one-pass cpu_baseline leg of the GPU arm")
     ap.add_argument("--ref-sample-clusters", type=int, default=16,
                     help="clusters per step of --impl reference (K + W steps must end within minutes)")
