@@ -13,12 +13,9 @@ namespace {
 constexpr int64_t kMaxChunkImages = 4096;
 // vg_classify projects up to this many images back to back before the tower runs over them in
 // chunks (26 GB of tiles at most): the projection is instruction bound, and between the tower's GEMMs
-// it would run at the SM clock the 1000 W cap leaves them (~1.1 GHz); on its own for a few
+// it would run at the SM clock the 1000 W cap leaves them (~1.05 GHz); on its own for a few
 // milliseconds the board clocks it up.  VG_PROJ_BATCH (images) overrides, e.g. 4096 = one chunk.
 constexpr int64_t kMaxProjImages = 262144;
-// per image: residual stream fp32 + one bf16 [197,768] buffer + one bf16 [197,3072] buffer
-constexpr size_t kEncodeBytesPerImage =
-    (size_t)kTokens * ((size_t)kWidth * 4 + (size_t)kWidth * 2 + (size_t)kMlp * 2);
 constexpr size_t kTileBytesPerImage = (size_t)VG_TILE_ELEMS * 2;
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
