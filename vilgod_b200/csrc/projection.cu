@@ -1480,11 +1480,17 @@ __device__ __forceinline__ void fast_image(const ProjParams &P, const int b, Fas
 #pragma unroll
         for (int i = 1; i < NWF; ++i) mx = fmaxf(mx, sm.red[i]);
         const float rc_mx = __frcp_rn(mx);
+        // 1 - t / mx with div_rn's three steps (q = t rc; r = t - mx q; q + r rc) on packed pairs: the same
+        // IEEE operations per element as the scalar form
+        const f32x2 rc2 = pack2(rc_mx, rc_mx), nmx2 = pack2(-mx, -mx), one2 = pack2(1.0f, 1.0f);
+        auto norm2 = [&](float a, float b, float &ra, float &rb) {
+            const f32x2 t = pack2(a, b);
+            const f32x2 q = mul2(t, rc2);
+            unpack2(sub2(one2, fma2(fma2(nmx2, q, t), rc2, q)), ra, rb);
+        };
         auto norm4 = [&](float4 t) {
-            t.x = __fsub_rn(1.0f, div_rn(t.x, mx, rc_mx, false));
-            t.y = __fsub_rn(1.0f, div_rn(t.y, mx, rc_mx, false));
-            t.z = __fsub_rn(1.0f, div_rn(t.z, mx, rc_mx, false));
-            t.w = __fsub_rn(1.0f, div_rn(t.w, mx, rc_mx, false));
+            norm2(t.x, t.y, t.x, t.y);
+            norm2(t.z, t.w, t.z, t.w);
             return t;
         };
         const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
