@@ -187,3 +187,37 @@ def test_fast_projection_kernel_closed_forms():
                 cols = np.flatnonzero(~((xb < lo) | (xa > hi)))
                 assert (cols.min(), cols.max()) == (first_with(lo - 1) >> 3,
                                                     min(min(first_with(hi + 1) - 1, S - 1) >> 3, NG - 1))
+
+
+def test_fast_projection_kernel_region_bound():
+    """projection_init sizes the fast kernel's shared-memory layout from obj_ratio: at the reference's 0.8
+    every occupied grid cell has X, Y in [ceil(R/2 (1-0.8)), ceil(R/2 (1+0.8))] = [12, 101] (R = 112) /
+    [23, 202] (R = 224), so the touched region (4 cells below, 2 above the occupied range) never exceeds
+    96 rows x 24 float4 strips / 186 x 48 and no image of a valid cluster is handed over for its geometry.
+    Checked on the oracle's points2grid over random, anisotropic and adversarial clusters and all ten views."""
+    from oracle import projection as op
+    from vilgod_b200 import synthetic
+    rng = np.random.default_rng(5)
+    clusters = []
+    pts, off = synthetic.make_clusters(60, n_min=2, n_max=600, rng=rng)
+    clusters += [pts[off[c]:off[c + 1]] for c in range(len(off) - 1)]
+    for scale in ((1, 1, 1), (50, 0.01, 0.01), (0.01, 50, 1), (1e-3, 1e-3, 1e3), (1e4, 1e4, 1e4)):
+        clusters.append((rng.uniform(-1, 1, size=(300, 3)) * np.asarray(scale)).astype(np.float32))
+    cube = np.stack(np.meshgrid(*[np.array([-1.0, 1.0])] * 3, indexing="ij"), -1).reshape(-1, 3)   # the corners
+    clusters.append(cube.astype(np.float32))
+    clusters.append((cube * np.array([3.0, 1.0, 0.2]) + 1e5).astype(np.float32))
+    rot = op.view_rot_mats(10)
+    for R, (lo, hi), (max_rows, max_strips) in ((112, (12, 101), (96, 24)), (224, (23, 202), (186, 48))):
+        Q = R - 2
+        for p in clusters:
+            for v in range(10):
+                q = op.rotate(p, rot[v], fused=9 * len(p) >= 400)
+                try:
+                    grid = op.points2grid(q, R=R)
+                except ValueError:
+                    continue                                  # degenerate (no extent): flagged, not projected
+                _, ys, xs = np.nonzero(grid)
+                assert lo <= ys.min() and ys.max() <= hi and lo <= xs.min() and xs.max() <= hi
+                ulo, uhi = max(ys.min() - 4, 0), min(ys.max() + 2, Q - 1)
+                vlo, vhi = max(xs.min() - 4, 0), min(xs.max() + 2, Q - 1)
+                assert uhi - ulo + 1 <= max_rows and (vhi >> 2) - (vlo >> 2) + 1 <= max_strips
