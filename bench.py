@@ -650,9 +650,10 @@ def run_ours(a):
     timed_label_hist = torch.bincount(out["voted_class"].clamp(min=0).long(), minlength=4).tolist()
 
     # --- timed region 2: same K steps with an event pair around every kernel launch ---
+    prof_steps = min(a.steps, 5)     # per-step figures; five steps are enough and keep a K = 20 run short
     eng.profile_begin()
     barrier()
-    for _ in range(a.steps):
+    for _ in range(prof_steps):
         step_resident()
         flush.zero_()
     barrier()
@@ -705,10 +706,10 @@ def run_ours(a):
                     "frac": gemm_tflops / peaks["bf16_tflops"], "traffic": traffic,
                     "peak_source": peaks["source"], "launches": g_n,
                     "avg_launch_ms": g_ms / max(g_n, 1), "share_of_step": g_ms / max(all_ms, 1e-9),
-                    "operand_dtype": a.operand_dtype,
+                    "operand_dtype": a.operand_dtype, "profiled_steps": prof_steps,
                     "cublas_sustained_tflops_this_board": cublas_ref}
         p = prof["projection"]
-        proj_bytes = p["work"] + 12.0 * total_points * a.steps
+        proj_bytes = p["work"] + 12.0 * total_points * prof_steps
         proj_gbs = proj_bytes / (p["ms"] * 1e-3) / 1e9 if p["ms"] > 0 else 0.0
         roofline_proj = {"bound": "hbm", "kernel": "projection_fast_kernel (+ projection_kernel in list mode for clusters > 2048 points), "
                                                     "whole batch projected before the tower", "achieved": proj_gbs,
@@ -722,7 +723,7 @@ def run_ours(a):
             tj = json.load(open(tp))
             # ncu measured one launch of 30000 images; the step launches 4090-cluster chunks: scale per image
             per_image = tj["dram_bytes_per_image"]
-            roofline_proj["traffic"] = per_image * C * V * a.steps / max(p["launches"], 1)
+            roofline_proj["traffic"] = per_image * C * V * prof_steps / max(p["launches"], 1)
             roofline_proj["traffic_note"] = (f"{per_image:.0f} B of DRAM traffic per image from one ncu --set full "
                                              f"capture (profiles/r02_projection_traffic.json) x images per launch")
             ptraffic = per_image * Cp * V
@@ -732,9 +733,9 @@ def run_ours(a):
                                "frac": pa_gbs / peaks["hbm_gbs"], "traffic": ptraffic, "launches": 5,
                                "avg_launch_ms": proj_alone_ms, "images_per_launch": Cp * V}
         vit_ms = all_ms - p["ms"] - prof["vote"]["ms"]
-        images = C * V * a.steps
+        images = C * V * prof_steps
         vit_frac = FLOP_PER_IMAGE * images / (vit_ms * 1e-3) / 1e12 / peaks["bf16_tflops"] if vit_ms > 0 else 0
-        breakdown = {k: {"ms_per_step": v["ms"] / a.steps, "launches_per_step": v["launches"] // a.steps}
+        breakdown = {k: {"ms_per_step": v["ms"] / prof_steps, "launches_per_step": v["launches"] // prof_steps}
                      for k, v in prof.items()}
         cpu_baseline = None
         if world == 1 and not a.no_cpu_baseline:
