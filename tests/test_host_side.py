@@ -189,6 +189,39 @@ def test_fast_projection_kernel_closed_forms():
                                                     min(min(first_with(hi + 1) - 1, S - 1) >> 3, NG - 1))
 
 
+def test_fast_projection_kernel_emit_source_window():
+    """The fast kernel writes the normalised image back into its bounding-box buffer (buffer row = y + 1 - ulo,
+    float column = x + 4 (2 - (vlo >> 2))) and fills with 1.0 only what the bilinear emit can read beside it:
+    rows 0 and nr + 1, nr + 2, and the strips 0, 1, ns + 2, ns + 3 of the image rows.
+    The emit reads source rows i0[oy], i0[oy] + 1 of the active output rows and source columns i0[ox],
+    i0[ox] + 1 of the active 8-pixel groups (unclamped at the last row / column, where the second weight is
+    exactly 0): checked exhaustively that this window is rows 0 .. nr + 1 x strips 0 .. ns + 3."""
+    S, NG = 224, 28
+    for R in (112, 224):
+        Q = R - 2
+        i0 = (np.arange(S) * (Q - 1)) // (S - 1)
+
+        def first_with(t):
+            return 0 if t <= 0 else (t * (S - 1) + (Q - 2)) // (Q - 1)
+
+        lo_seen, hi_seen = 99, -1
+        for lo in range(Q):
+            for hi in range(lo, Q):
+                # columns: lo, hi = vlo, vhi
+                ns = (hi >> 2) - (lo >> 2) + 1
+                g_lo, g_hi = first_with(lo - 1) >> 3, min(min(first_with(hi + 1) - 1, S - 1) >> 3, NG - 1)
+                ocol = 4 * (2 - (lo >> 2))
+                c_first, c_last = i0[8 * g_lo] + ocol, i0[8 * g_hi + 7] + 1 + ocol
+                assert 0 <= c_first and (c_last >> 2) <= ns + 3
+                lo_seen, hi_seen = min(lo_seen, c_first >> 2), max(hi_seen, (c_last >> 2) - ns)
+                # rows: lo, hi = ulo, uhi
+                nr = hi - lo + 1
+                oy_lo, oy_hi = first_with(lo - 1), min(first_with(hi + 1) - 1, S - 1)
+                r_first, r_last = i0[oy_lo] + 1 - lo, i0[oy_hi] + 1 + 1 - lo
+                assert 0 <= r_first and r_last <= nr + 1
+        assert (lo_seen, hi_seen) == (0, 3)       # the four margin strips are all needed
+
+
 def test_fast_projection_kernel_region_bound():
     """projection_init sizes the fast kernel's shared-memory layout from obj_ratio: at the reference's 0.8
     every occupied grid cell has X, Y in [ceil(R/2 (1-0.8)), ceil(R/2 (1+0.8))] = [12, 101] (R = 112) /

@@ -160,7 +160,7 @@ def test_stamp_and_dense_paths_agree(engines):
 def test_fast_and_general_kernels_agree(monkeypatch):
     """The fast kernel (register-resident image, bounding-box buffer, walking emit; clusters up to 2048
     points) hands larger clusters over to the general kernel in list mode.  Every variant of it
-    (VG_PROJ_VARIANT 1 / 2 / 3) must produce the bits of the general kernel alone (variant 0) and of the
+    (VG_PROJ_VARIANT 1 = default, 2 = previous emit) must produce the bits of the general kernel alone (variant 0) and of the
     oracle, for tiles, uint8 (all views and first view only) and the densified tap."""
     from vilgod_b200 import synthetic
     from vilgod_b200.engine import Engine
@@ -177,13 +177,15 @@ def test_fast_and_general_kernels_agree(monkeypatch):
     off = np.concatenate(offs).astype(np.int32)
     V = 10
     outs = {}
-    for variant in ("0", "1", "2", "3"):
+    for variant in ("0", "1", "2"):
         monkeypatch.setenv("VG_PROJ_VARIANT", variant)
         eng = Engine(num_views=V)
         try:
             outs[variant] = eng.project(pts, off, want_u8=True, want_densified=True)
             again = eng.project(pts, off, want_u8=True)
             assert torch.equal(outs[variant]["tiles"], again["tiles"])
+            only = eng.project(pts, off)           # the production call: tiles, no uint8 image
+            assert torch.equal(outs[variant]["tiles"], only["tiles"])
         finally:
             eng.close()
     ref = outs["0"]
@@ -191,7 +193,7 @@ def test_fast_and_general_kernels_agree(monkeypatch):
     ok = st == 0                       # single-point clusters have no extent: flagged, taps not written
     assert ok.sum() >= len(st) - 6
     okt = torch.as_tensor(ok, device=ref["status"].device)
-    for variant in ("1", "2", "3"):
+    for variant in ("1", "2"):
         o = outs[variant]
         assert torch.equal(o["status"], ref["status"]), variant
         assert torch.equal(o["tiles"], ref["tiles"]), variant
@@ -208,16 +210,20 @@ def test_fast_and_general_kernels_agree(monkeypatch):
     assert torch.equal(tiles_to_u8(outs["1"]["tiles"]), outs["1"]["u8"])
     # R = 224 (BASELINE configs[3]): the fast kernel's 512-thread instantiation against the general kernel
     r224 = {}
-    for variant in ("0", "1"):
+    for variant in ("0", "1", "2"):
         monkeypatch.setenv("VG_PROJ_VARIANT", variant)
         eng = Engine(num_views=6, resolution=224)
         try:
             r224[variant] = eng.project(pts, off, want_u8=True, want_densified=True)
+            r224[variant]["tiles_only"] = eng.project(pts, off)["tiles"]     # the production call: no uint8 image
         finally:
             eng.close()
-    assert torch.equal(r224["1"]["status"], r224["0"]["status"])
-    assert torch.equal(r224["1"]["tiles"], r224["0"]["tiles"]) and torch.equal(r224["1"]["u8"], r224["0"]["u8"])
-    assert torch.equal(r224["1"]["densified"].reshape(C, -1)[okt], r224["0"]["densified"].reshape(C, -1)[okt])
+    for variant in ("1", "2"):
+        a, b = r224[variant], r224["0"]
+        assert torch.equal(a["status"], b["status"]), variant
+        assert torch.equal(a["tiles"], b["tiles"]) and torch.equal(a["u8"], b["u8"]), variant
+        assert torch.equal(a["tiles_only"], b["tiles"]), variant
+        assert torch.equal(a["densified"].reshape(C, -1)[okt], b["densified"].reshape(C, -1)[okt]), variant
 
 
 def test_r224_grid_against_reference_and_oracle(golden, engines):

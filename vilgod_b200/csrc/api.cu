@@ -188,7 +188,7 @@ int vg_create(const VgConfig *cfg, VgHandle **out)
         if (v >= 1) h->proj_batch_images = v < kMaxProjImages ? v : kMaxProjImages;
     }
     if (const char *pv = getenv("VG_PROJ_VARIANT"))
-        if (pv[0] >= '0' && pv[0] <= '3' && pv[1] == 0) h->sw.proj_variant = pv[0] - '0';
+        if (pv[0] >= '0' && pv[0] <= '2' && pv[1] == 0) h->sw.proj_variant = pv[0] - '0';
     if (env_on("VG_ATTN_TRACE") && cudaMalloc(&h->attn_trace, 16 * 8 * sizeof(long long)) != cudaSuccess)
         h->attn_trace = nullptr;
     *out = h;

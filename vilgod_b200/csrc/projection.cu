@@ -1008,7 +1008,7 @@ __global__ void __launch_bounds__(NT, R == 112 ? 2 : 1) projection_kernel(const 
 // whose touched region is at most F_MAXR rows x F_MAXS float4 strips (always, at the reference's
 // obj_ratio = 0.8: X, Y in [12, 101]).  Same arithmetic as project_image's stamp path -- the results
 // are bit-identical -- organised for instruction count:
-//   * 256-thread CTAs, ~63 KB of shared memory -> three CTAs per SM: half the per-warp replicated
+//   * 256-thread CTAs, 74 KB of shared memory -> three CTAs per SM: half the per-warp replicated
 //     overhead of the 512-thread kernel, and three independent barrier domains per SM.
 //   * rotated points stay in registers between the min / max pass and the quantisation.
 //   * ONE bounding-box-limited buffer B (origin = the union of all slices' touched regions, fixed
@@ -1021,8 +1021,12 @@ __global__ void __launch_bounds__(NT, R == 112 ? 2 : 1) projection_kernel(const 
 //     bilinear emit WALKS: a thread owns one 8-pixel column group and a run of output rows, keeps the
 //     horizontally interpolated source rows y0 / y0 + 1 in registers and advances them as the run
 //     moves down -- no intermediate buffer, no barrier, every horizontal interpolation done ~once.
+//     Its tables are laid out for the loop: the column weights as the packed pairs FFMA2 consumes (one
+//     8-byte load, nothing to re-pack per row) and one 16-byte record per output row (both weights, the
+//     next row's source row, the row's byte offset in the tile); when only tiles are wanted the row loop
+//     carries no pointer tests: 21 instead of 34 instructions per emitted row of four pixels.
 constexpr int FAST_N = 2048;
-// largest touched region the path takes (rows x float4 strips) and its buffer.  R = 112: 96 x 24 (63 KB per
+// largest touched region the path takes (rows x float4 strips) and its buffer.  R = 112: 96 x 24 (74 KB per
 // CTA, three 256-thread CTAs per SM).  R = 224 (BASELINE configs[3]): 186 x 48 (X, Y in [23, 202]), 187 KB:
 // one 512-thread CTA per SM with nine (row pair, strip) items per thread in its 128 registers.
 template <int R> struct FastGeo {
@@ -1042,9 +1046,19 @@ template <int R> struct FastSmem {
     int degenerate;
     int next;              // next image of this CTA (persistent loop)
     uint4 bgsrc[448];      // one patch row (14 patches x 512 B) of background pixels: source of the bulk stores
-    float2 lw[S];          // bilinear weights (l0, l1) of output row / column i ...
-    unsigned char i0[S];   // ... and its first source row / column (copy of ProjTables, filled per CTA)
+    union {
+        float2 lw[S];      // TAB = 0: bilinear weights (l0, l1) of output row / column i
+        struct {           // TAB = 1: the column weights as the packed pairs the emit multiplies with:
+            float2 cw0[S / 2], cw1[S / 2];     // cw0[k] = (l0[2k], l0[2k + 1]), cw1[k] = (l1[2k], l1[2k + 1])
+        };
+    };
+    float4 rowrec[S];      // TAB = 1, per output row: (l0, l1, first source row of the NEXT output row, byte
+                           // offset of the row inside a patch-major tile) -- one 16-byte load per emitted row
+    unsigned char i0[S];   // first source row / column of output row / column i (copy of ProjTables, per CTA)
 };
+// three CTAs per SM at R = 112: 228 KB of shared memory per SM, 1 KB reserved per CTA
+static_assert(sizeof(FastSmem<112>) <= (233472 / 3 - 1024), "FastSmem<112> must leave room for three CTAs per SM");
+static_assert(sizeof(FastSmem<224>) <= 232448, "FastSmem<224> exceeds the shared memory of an SM");
 
 // shared -> global bulk copy (TMA, no tensor map): the copy engine reads shared memory and writes L2
 // without passing through the load/store unit
@@ -1072,7 +1086,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 // one image (cluster b / V, view b % V); the bilinear table and the constant background row in `sm` were
 // filled by the kernel before its image loop
-template <int R, int NTF, int CW, int STAMP>
+template <int R, int NTF, int CW, int STAMP, int TAB>
 __device__ __forceinline__ void fast_image(const ProjParams &P, const int b, FastSmem<R> &sm)
 {
     constexpr int Q = R - 2, NS = R / 4, MW = (R + 31) / 32;
@@ -1494,7 +1508,20 @@ __device__ __forceinline__ void fast_image(const ProjParams &P, const int b, Fas
             return t;
         };
         const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (F_PITCH <= 32) {            // a lane per strip
+        if (TAB != 0) {
+            // the halo rows 0, nr + 1, nr + 2 whole (a warp each); of the image rows only the four strips
+            // beside the items that the emit can read -- 0, 1, ns + 2, ns + 3 (its source columns lie
+            // within strips 0 .. ns + 3 for every (vlo, vhi): tests/test_host_side.py) -- item-wise
+            static_assert(NWF >= 3, "one warp per halo row");
+            if (warp < 3) {
+                const int rb = warp == 0 ? 0 : nr + warp;
+                for (int sb = lane; sb < F_PITCH; sb += 32) sm.B[rb * F_PITCH + sb] = one4;
+            }
+            for (int item = tid; item < 4 * nr; item += NTF) {
+                const int rb = 1 + (item >> 2), e = item & 3;
+                sm.B[rb * F_PITCH + (e < 2 ? e : ns + e)] = one4;
+            }
+        } else if (F_PITCH <= 32) {     // a lane per strip
             if (lane < F_PITCH) {
                 const bool edge = lane < 2 || lane >= ns + 2;
                 for (int rb = warp; rb < nr + 3; rb += NWF)
@@ -1565,9 +1592,14 @@ __device__ __forceinline__ void fast_image(const ProjParams &P, const int b, Fas
         for (int j = 0; j < CP; ++j) {
             xa[2 * j] = b0 + 4u * sm.i0[ox0 + 2 * j];
             xa[2 * j + 1] = b0 + 4u * sm.i0[ox0 + 2 * j + 1];
-            const float2 ta = sm.lw[ox0 + 2 * j], tb = sm.lw[ox0 + 2 * j + 1];
-            lw0[j] = pack2(ta.x, tb.x);
-            lw1[j] = pack2(ta.y, tb.y);
+            if (TAB == 0) {
+                const float2 ta = sm.lw[ox0 + 2 * j], tb = sm.lw[ox0 + 2 * j + 1];
+                lw0[j] = pack2(ta.x, tb.x);
+                lw1[j] = pack2(ta.y, tb.y);
+            } else {        // the pairs as stored: one 8-byte load each, nothing to re-pack in the row loop
+                lw0[j] = *reinterpret_cast<const f32x2 *>(&sm.cw0[(ox0 >> 1) + j]);
+                lw1[j] = *reinterpret_cast<const f32x2 *>(&sm.cw1[(ox0 >> 1) + j]);
+            }
         }
         f32x2 ha[CP], hb[CP];
         auto hrow = [&](int y, f32x2 (&h)[CP]) {
@@ -1586,10 +1618,21 @@ __device__ __forceinline__ void fast_image(const ProjParams &P, const int b, Fas
         op_t *tdst = tile ? tile + (ox0 >> 4) * 256 + (ox0 & 15) : nullptr;
         int ynext = sm.i0[oy];             // upper source row of output row oy, loaded one row ahead
         // the output rows whose upper source row is y, from top = HI[y] and bot = HI[y + 1]
-        auto emit_rows = [&](int y, const f32x2 (&top)[CP], const f32x2 (&bot)[CP]) {
+        // `kTilesOnly` (a constant at both call sites once `walk` is inlined): the caller wants the tile and
+        // no uint8 image -- the production case -- so the row loop carries neither pointer test (TAB = 1)
+        auto emit_rows = [&](const bool kTilesOnly, int y, const f32x2 (&top)[CP], const f32x2 (&bot)[CP]) {
             while (oy <= oy_hi && ynext == y) {
-                const float2 lh = sm.lw[oy];
-                ynext = sm.i0[min(oy + 1, S - 1)];
+                float2 lh;
+                int toff = 0;               // byte offset of row oy inside the tile
+                if (TAB == 0) {
+                    lh = sm.lw[oy];
+                    ynext = sm.i0[min(oy + 1, S - 1)];
+                } else {
+                    const float4 rec = sm.rowrec[oy];
+                    lh = make_float2(rec.x, rec.y);
+                    ynext = __float_as_int(rec.z);
+                    toff = __float_as_int(rec.w);
+                }
                 const f32x2 h0 = pack2(lh.x, lh.x), h1 = pack2(lh.y, lh.y);
                 unsigned fb[CW];
 #pragma unroll
@@ -1601,7 +1644,7 @@ __device__ __forceinline__ void fast_image(const ProjParams &P, const int b, Fas
                     fb[2 * j] = __float_as_uint(q0);
                     fb[2 * j + 1] = __float_as_uint(q1);
                 }
-                if (tdst) {
+                if (kTilesOnly || tdst) {
                     unsigned pk[CP];
 #pragma unroll
                     for (int j = 0; j < CP; ++j) {
@@ -1611,12 +1654,13 @@ __device__ __forceinline__ void fast_image(const ProjParams &P, const int b, Fas
                         pk[j] = __byte_perm(fb[2 * j], fb[2 * j + 1], 0x7632);   // integers 0..255: high halves
 #endif
                     }
-                    op_t *dst = tdst + (oy >> 4) * (14 * 256) + (oy & 15) * 16;
+                    op_t *dst = TAB == 0 ? tdst + (oy >> 4) * (14 * 256) + (oy & 15) * 16
+                                         : reinterpret_cast<op_t *>(reinterpret_cast<char *>(tdst) + toff);
                     if (CW == 8) *reinterpret_cast<uint4 *>(dst) = make_uint4(pk[0], pk[1 % CP], pk[2 % CP], pk[3 % CP]);
                     else if (CW == 4) *reinterpret_cast<uint2 *>(dst) = make_uint2(pk[0], pk[1 % CP]);
                     else *reinterpret_cast<unsigned *>(dst) = pk[0];
                 }
-                if (u8) {
+                if (!kTilesOnly && u8) {
                     uint8_t *dst = u8 + oy * S + ox0;
                     unsigned w0 = 0, w1 = 0;
 #pragma unroll
@@ -1632,15 +1676,19 @@ __device__ __forceinline__ void fast_image(const ProjParams &P, const int b, Fas
             }
         };
         // two source rows per trip, the two row buffers swapping roles (no register copies)
-        hrow(ys, ha);
-        for (int y = ys;;) {
-            hrow(y + 1, hb);
-            emit_rows(y, ha, hb);
-            if (++y > ye) break;
-            hrow(y + 1, ha);
-            emit_rows(y, hb, ha);
-            if (++y > ye) break;
-        }
+        auto walk = [&](const bool tiles_only) {
+            hrow(ys, ha);
+            for (int y = ys;;) {
+                hrow(y + 1, hb);
+                emit_rows(tiles_only, y, ha, hb);
+                if (++y > ye) break;
+                hrow(y + 1, ha);
+                emit_rows(tiles_only, y, hb, ha);
+                if (++y > ye) break;
+            }
+        };
+        if (TAB != 0 && tdst && !u8) walk(true);
+        else walk(false);
         VG_TR(8);
     }
 }
@@ -1648,7 +1696,7 @@ __device__ __forceinline__ void fast_image(const ProjParams &P, const int b, Fas
 // Persistent CTAs (three per SM): the bilinear table and the constant background row are set up once,
 // then images are drawn from a counter (they differ a lot in cost); the next index is fetched before the
 // barrier that ends an image, so the loop adds one barrier per image and no exposed latency.
-template <int R, int NTF, int MINB, int CW, int STAMP>
+template <int R, int NTF, int MINB, int CW, int STAMP, int TAB>
 __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjParams P, const int images)
 {
     static_assert(NTF >= S && NTF >= 64, "setup roles are mapped to thread ids");
@@ -1656,14 +1704,22 @@ __global__ void __launch_bounds__(NTF, MINB) projection_fast_kernel(const ProjPa
     FastSmem<R> &sm = *reinterpret_cast<FastSmem<R> *>(smem_raw);
     const int tid = threadIdx.x;
     if (tid < S) {
-        sm.lw[tid] = make_float2(__ldg(&P.tab->l0[tid]), __ldg(&P.tab->l1[tid]));
+        const float l0 = __ldg(&P.tab->l0[tid]), l1 = __ldg(&P.tab->l1[tid]);
         sm.i0[tid] = (unsigned char)__ldg(&P.tab->i0[tid]);
+        if (TAB == 0) {
+            sm.lw[tid] = make_float2(l0, l1);
+        } else {
+            reinterpret_cast<float *>(sm.cw0)[tid] = l0;
+            reinterpret_cast<float *>(sm.cw1)[tid] = l1;
+            sm.rowrec[tid] = make_float4(l0, l1, __int_as_float(__ldg(&P.tab->i0[min(tid + 1, S - 1)])),
+                                         __int_as_float(2 * ((tid >> 4) * (14 * 256) + (tid & 15) * 16)));
+        }
     }
     if (P.bg_splat != 0u && P.tiles)
         for (int i = tid; i < 448; i += NTF) sm.bgsrc[i] = make_uint4(P.bg_splat, P.bg_splat, P.bg_splat, P.bg_splat);
     int i = (int)blockIdx.x;
     while (i < images) {
-        fast_image<R, NTF, CW, STAMP>(P, P.block0 + i, sm);
+        fast_image<R, NTF, CW, STAMP, TAB>(P, P.block0 + i, sm);
         if (tid == 0) sm.next = (int)gridDim.x + atomicAdd(&P.defer[2], 1);
         __syncthreads();       // the image is finished by every warp; the next one re-initialises `sm`
         i = sm.next;
@@ -1679,14 +1735,14 @@ int launch_projection_t(VgHandle *h, const ProjParams &P, long long blocks, cuda
     return VG_OK;
 }
 
-template <int R, int NTF, int MINB, int CW, int STAMP>
+template <int R, int NTF, int MINB, int CW, int STAMP, int TAB>
 int launch_fast_t(VgHandle *h, const ProjParams &P, long long blocks, cudaStream_t st)
 {
-    int rc = vg_set_smem_once(h, reinterpret_cast<const void *>(projection_fast_kernel<R, NTF, MINB, CW, STAMP>),
+    int rc = vg_set_smem_once(h, reinterpret_cast<const void *>(projection_fast_kernel<R, NTF, MINB, CW, STAMP, TAB>),
                               sizeof(FastSmem<R>));
     if (rc) return rc;
     const long long grid = std::min<long long>(blocks, (long long)MINB * h->num_sms);
-    projection_fast_kernel<R, NTF, MINB, CW, STAMP><<<(unsigned)grid, NTF, sizeof(FastSmem<R>), st>>>(P, (int)blocks);
+    projection_fast_kernel<R, NTF, MINB, CW, STAMP, TAB><<<(unsigned)grid, NTF, sizeof(FastSmem<R>), st>>>(P, (int)blocks);
     return VG_OK;
 }
 
@@ -1832,12 +1888,14 @@ int launch_projection(VgHandle *h, const float *d_points, const int32_t *d_offse
             VG_CUDA_CHECK(h, cudaMemsetAsync(P.defer, 0, 3 * sizeof(int32_t), st));
             P.block0 = (int32_t)b0;
             if (cfg.resolution == 224) {
-                rc = launch_fast_t<224, 512, 1, 4, 1>(h, P, nb, st);
+                switch (h->sw.proj_variant) {
+                case 2: rc = launch_fast_t<224, 512, 1, 4, 1, 0>(h, P, nb, st); break;
+                default: rc = launch_fast_t<224, 512, 1, 4, 1, 1>(h, P, nb, st); break;
+                }
             } else {
                 switch (h->sw.proj_variant) {
-                case 2: rc = launch_fast_t<112, 256, 3, 4, 0>(h, P, nb, st); break;
-                case 3: rc = launch_fast_t<112, 256, 3, 8, 1>(h, P, nb, st); break;
-                default: rc = launch_fast_t<112, 256, 3, 4, 1>(h, P, nb, st); break;
+                case 2: rc = launch_fast_t<112, 256, 3, 4, 1, 0>(h, P, nb, st); break;
+                default: rc = launch_fast_t<112, 256, 3, 4, 1, 1>(h, P, nb, st); break;
                 }
             }
             if (rc) return rc;
