@@ -14,7 +14,7 @@ C = len(off) - 1
 d_p, d_o = torch.from_numpy(pts).cuda(), torch.from_numpy(off).cuda()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 by = 12.0 * int(off[-1]) + C * V * 100352.0
-for R, variants, rounds in ((112, "12341234", 7), (224, "1414", 5)):
+for R, variants, rounds in ((112, "131313", 7), (224, "1313", 5)):
     for v in variants:
         os.environ["VG_PROJ_VARIANT"] = v
         eng = Engine(num_views=V, resolution=R)

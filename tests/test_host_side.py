@@ -220,6 +220,10 @@ def test_fast_projection_kernel_emit_source_window():
                 r_first, r_last = i0[oy_lo] + 1 - lo, i0[oy_hi] + 1 + 1 - lo
                 assert 0 <= r_first and r_last <= nr + 1
         assert (lo_seen, hi_seen) == (0, 3)       # the four margin strips are all needed
+        # the four output columns of an emit thread start at source columns s + (0, d1, d2, d3): the patterns
+        # the run-load form of the horizontal interpolation selects from
+        pats = {tuple(int(i0[o + j] - i0[o]) for j in range(1, 4)) for o in range(0, S, 4)}
+        assert pats == ({(0, 0, 1), (0, 1, 1), (1, 1, 1), (1, 1, 2)} if R == 112 else {(0, 1, 2), (1, 2, 3)})
 
 
 def test_fast_projection_kernel_region_bound():

@@ -122,9 +122,9 @@ struct VgHandle {
         bool ln_unfused = false;    // VG_LN_UNFUSED=1: separate LayerNorm kernels instead of the folded GEMMs
         bool gemm_narrow = false;   // VG_GEMM_NARROW=1: 4-warp / 4-stage residual epilogues everywhere
         int proj_variant = 1;       // VG_PROJ_VARIANT: 0 = general kernel only, 1 = fast kernel (default: emit from
-                                    // packed column-weight / row-record tables, item-wise margin fill, row loop
-                                    // without pointer tests when only tiles are wanted), 2 = fast kernel with the
-                                    // previous emit (A/B)
+                                    // packed column-weight / row-record tables, run-loaded source pixels, item-wise
+                                    // margin fill, row loop without pointer tests when only tiles are wanted),
+                                    // 2 = fast kernel with the previous emit (A/B)
     } sw;
     long long *attn_trace = nullptr;   // VG_ATTN_TRACE: clock64 stamps of CTA 0 (attention_tcgen05.cu)
 };

@@ -1024,7 +1024,10 @@ __global__ void __launch_bounds__(NT, R == 112 ? 2 : 1) projection_kernel(const 
 //     Its tables are laid out for the loop: the column weights as the packed pairs FFMA2 consumes (one
 //     8-byte load, nothing to re-pack per row) and one 16-byte record per output row (both weights, the
 //     next row's source row, the row's byte offset in the tile); when only tiles are wanted the row loop
-//     carries no pointer tests: 21 instead of 34 instructions per emitted row of four pixels.
+//     carries no pointer tests: 21 instead of 34 instructions per emitted row of four pixels.  The
+//     horizontal pass loads the run of 4 (5) source floats its four columns draw from ONCE and picks the
+//     operands with per-thread byte-permute selectors: half the shared-memory wavefronts of eight scalar
+//     loads whose lanes are two floats apart.
 constexpr int FAST_N = 2048;
 // largest touched region the path takes (rows x float4 strips) and its buffer.  R = 112: 96 x 24 (74 KB per
 // CTA, three 256-thread CTAs per SM).  R = 224 (BASELINE configs[3]): 186 x 48 (X, Y in [23, 202]), 187 KB:
@@ -1602,8 +1605,42 @@ __device__ __forceinline__ void fast_image(const ProjParams &P, const int b, Fas
             }
         }
         f32x2 ha[CP], hb[CP];
+        // TAB = 1, four columns per thread: their first source columns are s = i0[ox0] plus (0, d1, d2, d3) with
+        // (d1, d2, d3) one of (0,0,1) (0,1,1) (1,1,1) (1,1,2) at R = 112 and (0,1,2) (1,2,3) at R = 224
+        // (tests/test_host_side.py), so the thread loads the run s .. s + 3 (4) ONCE -- one address, half the
+        // shared-memory wavefronts of eight scalar loads at stride 2 -- and picks its operands with
+        // per-thread constant selectors.  The last float of the run may lie one past what the scalar form reads: still
+        // inside the buffer row, never selected.
+        // (byte-permute selectors rather than predicates: one instruction per pick, nothing to rematerialise)
+        const unsigned s1 = sm.i0[ox0 + 1] != sm.i0[ox0] ? 0x7654u : 0x3210u,
+                       s2 = sm.i0[ox0 + 2] != sm.i0[ox0] ? 0x7654u : 0x3210u,
+                       s3 = (int)sm.i0[ox0 + 3] - (int)sm.i0[ox0] == 2 ? 0x7654u : 0x3210u;
+        auto pick = [](unsigned sel, float a, float b) {       // sel = 0x3210: a, 0x7654: b
+            return __uint_as_float(__byte_perm(__float_as_uint(a), __float_as_uint(b), sel));
+        };
         auto hrow = [&](int y, f32x2 (&h)[CP]) {
             const unsigned ro = (unsigned)(y * (4 * PW));
+            if (TAB != 0 && CW == 4 && R == 112) {
+                float v0, v1, v2, v3;
+                asm volatile("ld.shared.f32 %0, [%4];\n\tld.shared.f32 %1, [%4 + 4];\n\t"
+                             "ld.shared.f32 %2, [%4 + 8];\n\tld.shared.f32 %3, [%4 + 12];"
+                             : "=f"(v0), "=f"(v1), "=f"(v2), "=f"(v3) : "r"(xa[0] + ro));
+                h[0] = fma2(pack2(v0, pick(s1, v0, v1)), lw0[0], mul2(pack2(v1, pick(s1, v1, v2)), lw1[0]));
+                h[CP - 1] = fma2(pack2(pick(s2, v0, v1), pick(s3, v1, v2)), lw0[CP - 1],
+                                 mul2(pack2(pick(s2, v1, v2), pick(s3, v2, v3)), lw1[CP - 1]));
+                return;
+            }
+            if (TAB != 0 && CW == 4 && R == 224) {
+                float v0, v1, v2, v3, v4;
+                asm volatile("ld.shared.f32 %0, [%5];\n\tld.shared.f32 %1, [%5 + 4];\n\t"
+                             "ld.shared.f32 %2, [%5 + 8];\n\tld.shared.f32 %3, [%5 + 12];\n\t"
+                             "ld.shared.f32 %4, [%5 + 16];"
+                             : "=f"(v0), "=f"(v1), "=f"(v2), "=f"(v3), "=f"(v4) : "r"(xa[0] + ro));
+                h[0] = fma2(pack2(v0, pick(s1, v0, v1)), lw0[0], mul2(pack2(v1, pick(s1, v1, v2)), lw1[0]));
+                h[CP - 1] = fma2(pack2(pick(s1, v1, v2), pick(s1, v2, v3)), lw0[CP - 1],
+                                 mul2(pack2(pick(s1, v2, v3), pick(s1, v3, v4)), lw1[CP - 1]));
+                return;
+            }
 #pragma unroll
             for (int j = 0; j < CP; ++j) {
                 float a0, a1, c0, c1;
