@@ -1010,7 +1010,8 @@ __global__ void __launch_bounds__(NT, R == 112 ? 2 : 1) projection_kernel(const 
 // are bit-identical -- organised for instruction count:
 //   * 256-thread CTAs, 74 KB of shared memory -> three CTAs per SM: half the per-warp replicated
 //     overhead of the 512-thread kernel, and three independent barrier domains per SM.
-//   * rotated points stay in registers between the min / max pass and the quantisation.
+//   * the rotated points wait in the (still unused) slice buffer between the min / max pass and the
+//     quantisation: rolled point loops, small code.
 //   * ONE bounding-box-limited buffer B (origin = the union of all slices' touched regions, fixed
 //     pitch, zero halo) holds the pooled slice; the running depth-max image lives in REGISTERS: a
 //     thread owns up to KQ (row pair, strip) items of the union for the whole image, so a slice costs
@@ -1018,7 +1019,7 @@ __global__ void __launch_bounds__(NT, R == 112 ? 2 : 1) projection_kernel(const 
 //     pooled rows.  Neighbour columns arrive by shuffle (row starts / warp edges: one predicated load
 //     from the zero halo / the neighbouring warp's strip).
 //   * after the last slice the normalised image is written back into B (margins = 1.0) and the
-//     bilinear emit WALKS: a thread owns one 8-pixel column group and a run of output rows, keeps the
+//     bilinear emit WALKS: a thread owns four adjacent output columns and a run of source rows, keeps the
 //     horizontally interpolated source rows y0 / y0 + 1 in registers and advances them as the run
 //     moves down -- no intermediate buffer, no barrier, every horizontal interpolation done ~once.
 //     Its tables are laid out for the loop: the column weights as the packed pairs FFMA2 consumes (one
