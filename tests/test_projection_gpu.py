@@ -441,3 +441,40 @@ def test_unsupported_configurations_are_rejected():
     for kw in (dict(resolution=160), dict(pool_kernel=3), dict(pool_pad=2), dict(div_mode=7), dict(depth=6)):
         with pytest.raises(VilgodError):
             Engine(num_views=4, **kw)
+
+
+def test_size_independent_properties_at_scale(engines):
+    """Properties that hold bit for bit whatever the input (tests/test_oracle_properties.py pins them on the
+    oracle), here on 2000 Waymo-shaped clusters x 10 views through the fast kernel and the hand-over list:
+    point order and repeated points do not matter (scatter-max is order independent and idempotent), a
+    power-of-two scale cancels exactly in (p - centre) / range, and a cluster's images do not depend on its
+    neighbours in the packed batch."""
+    from vilgod_b200 import synthetic
+    rng = np.random.default_rng(4242)
+    pts, off = synthetic.make_clusters(2000, n_min=64, n_max=3000, rng=rng)     # >= 45 points: one bmm rule
+    C = len(off) - 1
+    eng = engines(10)
+    base = eng.project(pts, off)
+    assert int(base["status"].abs().sum()) == 0
+    # permuted points + every point twice, cluster by cluster
+    parts, noff = [], [0]
+    for c in range(C):
+        p = pts[off[c]:off[c + 1]]
+        perm = rng.permutation(len(p))
+        parts += [p[perm], p]
+        noff.append(noff[-1] + 2 * len(p))
+    dup = eng.project(np.concatenate(parts), np.asarray(noff, np.int32))
+    assert torch.equal(dup["tiles"], base["tiles"])
+    # power-of-two scales, a different one per cluster
+    k = rng.integers(-6, 9, size=C)
+    scale = np.repeat(np.exp2(k).astype(np.float32), np.diff(off))[:, None]
+    scaled = eng.project((pts * scale).astype(np.float32), off)
+    assert torch.equal(scaled["tiles"], base["tiles"])
+    # clusters in reverse order: images move with their cluster
+    order = np.arange(C)[::-1]
+    rp = np.concatenate([pts[off[c]:off[c + 1]] for c in order])
+    ro = np.zeros(C + 1, np.int32)
+    ro[1:] = np.cumsum([off[c + 1] - off[c] for c in order])
+    rev = eng.project(rp, ro)
+    V = 10
+    assert torch.equal(rev["tiles"].reshape(C, V, 196, 256).flip(0), base["tiles"].reshape(C, V, 196, 256))
